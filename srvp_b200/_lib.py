@@ -1,0 +1,72 @@
+"""ctypes binding of libsrvp_b200.so (the C ABI declared in include/srvp_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing or fails to load, importing any op
+raises. PyTorch is used for device memory and streams only; every pointer handed to the library is a
+`tensor.data_ptr()` and every call is enqueued on `torch.cuda.current_stream()`.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsrvp_b200.so')
+
+c_int = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_ptr = ctypes.c_void_p
+
+
+class ConvSrc(ctypes.Structure):
+    _fields_ = [('ptr', c_ptr), ('scale', c_ptr), ('shift', c_ptr), ('frame_map', c_ptr), ('channels', c_int),
+                ('cpitch', c_int), ('coff', c_int), ('mode', c_int), ('lrelu', c_int)]
+
+
+class Conv3x3Args(ctypes.Structure):
+    _fields_ = [('src', ConvSrc * 2), ('nsrc', c_int), ('wpack', c_ptr), ('frames', c_int), ('H', c_int), ('W', c_int),
+                ('cout', c_int), ('cout_padded', c_int), ('epilogue', c_int), ('out', c_ptr), ('out_cpitch', c_int),
+                ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr)]
+
+
+SRC_DIRECT, SRC_POOL2, SRC_UP2 = 0, 1, 2
+EPI_RAW_BF16, EPI_SIGMOID_NCHW_F32 = 0, 1
+
+_lib = None
+
+
+def lib():
+    """Returns the loaded library; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               f'or `make -C srvp_b200/csrc`. srvp_b200 has no CPU / PyTorch fallback.')
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.srvp_last_error.restype = ctypes.c_char_p
+        for name in EXPORTS:
+            getattr(_lib, name)  # AttributeError if the header and the library disagree
+    return _lib
+
+
+# every symbol declared in include/srvp_b200.h
+EXPORTS = [
+    'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
+    'srvp_pack_conv3x3_weights',
+]
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise RuntimeError(f'srvp_b200 {what} failed ({rc}): {lib().srvp_last_error().decode()}')
+
+
+def stream_ptr():
+    return c_ptr(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return c_ptr(0)
+    assert t.is_cuda and t.is_contiguous(), 'srvp_b200 kernels need contiguous CUDA tensors'
+    return c_ptr(t.data_ptr())

@@ -1,0 +1,531 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05 (sm_100a), forward and data-gradient.
+//
+// Replaces, for the VGG64 encoder/decoder of the reference (module/conv.py:198-220, :333-354):
+//   nn.Conv2d(.,.,3,1,1) / nn.ConvTranspose2d(.,.,3,1,1)          -> the MMA main loop
+//   nn.BatchNorm2d apply + nn.LeakyReLU(0.2) of the PREVIOUS block -> fused into the operand loader
+//   nn.MaxPool2d(2), nn.Upsample(2), torch.cat([h, skip], 1), skip gather/expand over time -> loader
+//   nn.BatchNorm2d batch statistics of THIS block                  -> per-tile (sum, sumsq) in the epilogue
+//   torch.sigmoid on the last decoder layer                        -> epilogue variant
+//
+// Geometry ("virtual pixel" space). Frames are stacked vertically with one shared zero row between them and
+// two zero columns appended to every row: Wp = W + 2, Hp = H + 1, v = (f*Hp + y)*Wp + x. In this space every
+// 3x3 tap is a constant offset (ky-1)*Wp + (kx-1), including across image borders (the pads are the zeros).
+// A CTA stages the activations of MT consecutive virtual pixels plus a (Wp+1)-pixel halo on both sides in
+// shared memory ONCE per 64 input channels, laid out [chunk of 8 channels][pixel][8] = the SWIZZLE_NONE
+// K-major canonical UMMA layout with 16 B per pixel. The A operand of tap (ky,kx) is then the same buffer
+// with its start address advanced by (ky*Wp + kx)*16 bytes: 9 taps re-use one staged tile, so global/L2
+// traffic for activations is ~1x instead of 9x and the loader has time to apply BN + LeakyReLU + pooling.
+// Outputs at pad positions are computed and discarded (W/(W+2) * H/(H+1) efficiency).
+//
+// Warp roles (persistent CTA, 320 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-7
+// activation loaders, warp 8 MMA issuer (one thread), warp 9 weight TMA-bulk issuer (one thread).
+// TMEM: 2 accumulator stages x (MT/128) x NB fp32 columns, so the epilogue of tile i overlaps tile i+1.
+#include "common.cuh"
+#include "../../include/srvp_b200.h"
+
+namespace srvp {
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kHaloStages = 2;
+
+struct SrcDev {
+  const __nv_bfloat16* ptr;
+  const float* scale;
+  const float* shift;
+  const int* frame_map;
+  int channels, cpitch, coff, mode, lrelu;
+};
+
+struct ConvDev {
+  SrcDev src[2];
+  int nsrc;
+  int stages0;  // K stages taken from src[0]
+  int nstages;  // total K stages
+  const __nv_bfloat16* wpack;
+  int F, H, W, Hp, Wp;
+  long long vtotal;  // F*Hp*Wp
+  int cout, num_nblk, num_mtiles;
+  int P;  // halo rows per stage = MT + 2*Wp + 2
+  __nv_bfloat16* out;
+  int out_cpitch, out_coff;
+  float* stats_partial;
+  float* out_f32;
+};
+
+__device__ __forceinline__ uint4 transform8(uint4 raw, const float* __restrict__ scale, const float* __restrict__ shift, int lrelu_flag) {
+  if (scale == nullptr && !lrelu_flag) return raw;
+  float v[8];
+  {
+    float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  if (scale != nullptr) {
+    float4 s0 = __ldg(reinterpret_cast<const float4*>(scale)), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 1);
+    float4 h0 = __ldg(reinterpret_cast<const float4*>(shift)), h1 = __ldg(reinterpret_cast<const float4*>(shift) + 1);
+    v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+    v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+  }
+  if (lrelu_flag) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = lrelu(v[i]);
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+  uint4 o;
+  __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) po[i] = __hmax2(pa[i], pb[i]);
+  return o;
+}
+
+template <int NB, int MT, int KCH, int TPS, int EPI>
+struct Cfg {
+  static constexpr int MBLK = MT / 128;
+  static constexpr int WSLOTS = (KCH != 8) ? 2 : (NB >= 256 ? 3 : 4);
+  static constexpr int SLOT_BYTES = TPS * KCH * NB * 16;
+  static constexpr int STAGE_PITCH = NB * 2 + 16;  // bytes per staged output row
+  static constexpr int STAGING_BYTES = (EPI == SRVP_EPI_RAW_BF16) ? 128 * STAGE_PITCH : 0;
+  static constexpr int ACC_COLS = MBLK * NB;  // per accumulator stage
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(9 % TPS == 0, "taps per slot must divide 9");
+  static size_t smem_bytes(int P) {
+    return (size_t)kHaloStages * KCH * P * 16 + (size_t)WSLOTS * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 64 * 8 + 16;
+  }
+};
+
+template <int NB, int MT, int KCH, int TPS, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
+  using C = Cfg<NB, MT, KCH, TPS, EPI>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int P = p.P;
+  uint8_t* halo = smem;
+  uint8_t* wslots = halo + (size_t)kHaloStages * KCH * P * 16;
+  uint8_t* staging = wslots + (size_t)C::WSLOTS * C::SLOT_BYTES;
+  int* rowpix = reinterpret_cast<int*>(staging + C::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowpix + 128);
+  uint64_t* halo_full = bars;                    // [kHaloStages]
+  uint64_t* halo_empty = bars + kHaloStages;     // [kHaloStages]
+  uint64_t* w_full = bars + 2 * kHaloStages;     // [WSLOTS]
+  uint64_t* w_empty = w_full + C::WSLOTS;        // [WSLOTS]
+  uint64_t* acc_full = w_empty + C::WSLOTS;      // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < kHaloStages; ++i) { mbar_init(&halo_full[i], 128); mbar_init(&halo_empty[i], 1); }
+    for (int i = 0; i < C::WSLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_mtiles * p.num_nblk;
+  const int HpWp = p.Hp * p.Wp;
+
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ activation loaders
+    const int lt = tid - 128;
+    uint32_t it = 0;  // halo stage iteration counter
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mtile = tile / p.num_nblk;
+      const long long vbase = (long long)mtile * MT - p.Wp - 1;
+      for (int s = 0; s < p.nstages; ++s, ++it) {
+        const int hs = it % kHaloStages;
+        const bool second = s >= p.stages0;
+        const SrcDev& sd = p.src[second ? 1 : 0];
+        const int cb = second ? s - p.stages0 : s;
+        const int cloc = cb * KCH * 8;  // first channel of this stage within the source's consumed range
+        mbar_wait(&halo_empty[hs], ((it / kHaloStages) & 1) ^ 1);
+        uint8_t* hbuf = halo + (size_t)hs * KCH * P * 16;
+        for (int r = lt; r < P; r += 128) {
+          const long long vin = vbase + r;
+          bool valid = vin >= 0 && vin < p.vtotal;
+          int f = 0, y = 0, x = 0;
+          if (valid) {
+            f = (int)(vin / HpWp);
+            const int rem = (int)(vin - (long long)f * HpWp);
+            y = rem / p.Wp;
+            x = rem - y * p.Wp;
+            valid = (y < p.H) && (x < p.W);
+          }
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = make_uint4(0, 0, 0, 0);
+            continue;
+          }
+          const int fs = sd.frame_map ? __ldg(sd.frame_map + f) : f;
+          const float* sc = sd.scale ? sd.scale + cloc : nullptr;
+          const float* sh = sd.shift ? sd.shift + cloc : nullptr;
+          if (sd.mode == SRVP_SRC_POOL2) {
+            const int Ws = p.W * 2;
+            const __nv_bfloat16* base = sd.ptr + (((size_t)fs * (p.H * 2) + 2 * y) * Ws + 2 * x) * sd.cpitch + sd.coff + cloc;
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) {
+              const uint4 r00 = __ldg(reinterpret_cast<const uint4*>(base + j * 8));
+              const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(base + sd.cpitch + j * 8));
+              const uint4 r10 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * sd.cpitch + j * 8));
+              const uint4 r11 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(Ws + 1) * sd.cpitch + j * 8));
+              const float* scj = sc ? sc + j * 8 : nullptr;
+              const float* shj = sh ? sh + j * 8 : nullptr;
+              uint4 a = max8(max8(transform8(r00, scj, shj, sd.lrelu), transform8(r01, scj, shj, sd.lrelu)),
+                             max8(transform8(r10, scj, shj, sd.lrelu), transform8(r11, scj, shj, sd.lrelu)));
+              *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = a;
+            }
+          } else {
+            const __nv_bfloat16* base;
+            if (sd.mode == SRVP_SRC_UP2) {
+              base = sd.ptr + (((size_t)fs * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * sd.cpitch + sd.coff + cloc;
+            } else {
+              base = sd.ptr + (((size_t)fs * p.H + y) * p.W + x) * sd.cpitch + sd.coff + cloc;
+            }
+            uint4 raw[KCH];
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + j * 8));
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) {
+              *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) =
+                  transform8(raw[j], sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr, sd.lrelu);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&halo_full[hs]);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NB, 0, 0);
+      uint32_t hit = 0, wit = 0, tcount = 0;
+      const uint32_t halo_addr = smem_u32(halo), w_addr = smem_u32(wslots);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int as = tcount & 1;
+        mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * C::ACC_COLS;
+        for (int s = 0; s < p.nstages; ++s, ++hit) {
+          const int hs = hit % kHaloStages;
+          mbar_wait(&halo_full[hs], (hit / kHaloStages) & 1);
+          tc_fence_after();
+          const uint32_t hbase = halo_addr + hs * KCH * P * 16;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ws = wit % C::WSLOTS;
+            if (tap % TPS == 0) {
+              mbar_wait(&w_full[ws], (wit / C::WSLOTS) & 1);
+              tc_fence_after();
+            }
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const uint32_t wbase = w_addr + ws * C::SLOT_BYTES + (tap % TPS) * KCH * NB * 16;
+#pragma unroll
+            for (int mb = 0; mb < C::MBLK; ++mb) {
+              const uint32_t abase = hbase + (mb * 128 + ky * p.Wp + kx) * 16;
+#pragma unroll
+              for (int k = 0; k < KCH / 2; ++k) {
+                const uint64_t ad = umma_desc(abase + k * 2 * P * 16, P * 16, 128);
+                const uint64_t bd = umma_desc(wbase + k * 2 * NB * 16, NB * 16, 128);
+                umma_bf16(acc + mb * NB, ad, bd, idesc, (s | tap | k) != 0);
+              }
+            }
+            if (tap % TPS == TPS - 1) {
+              umma_commit(&w_empty[ws]);
+              ++wit;
+            }
+          }
+          umma_commit(&halo_empty[hs]);
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ weight loader (TMA bulk copies)
+    if (lane == 0) {
+      uint32_t wit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nblk = tile % p.num_nblk;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)nblk * p.nstages * 9 * KCH * NB * 16;
+        for (int s = 0; s < p.nstages; ++s) {
+          for (int q = 0; q < 9 / TPS; ++q, ++wit) {
+            const int ws = wit % C::WSLOTS;
+            mbar_wait(&w_empty[ws], ((wit / C::WSLOTS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
+            bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3)
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int mtile = tile / p.num_nblk, nblk = tile % p.num_nblk;
+      const int as = tcount & 1;
+      mbar_wait(&acc_full[as], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
+      constexpr int CPT = (NB + 127) / 128;  // stat columns per thread
+      float s1[CPT], s2[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) s1[i] = s2[i] = 0.f;
+
+#pragma unroll 1
+      for (int mb = 0; mb < C::MBLK; ++mb) {
+        const long long v = (long long)mtile * MT + mb * 128 + tid;
+        int f = 0, y = 0, x = 0;
+        bool valid = v < p.vtotal;
+        if (valid) {
+          f = (int)(v / HpWp);
+          const int rem = (int)(v - (long long)f * HpWp);
+          y = rem / p.Wp;
+          x = rem - y * p.Wp;
+          valid = (y < p.H) && (x < p.W);
+        }
+        if constexpr (EPI == SRVP_EPI_SIGMOID_NCHW_F32) {
+          float vals[16];
+          tmem_ld16(acc + mb * NB, vals);
+          if (mb == C::MBLK - 1) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
+          }
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              if (c < p.cout) {
+                const float sg = 1.f / (1.f + __expf(-vals[c]));
+                p.out_f32[(((size_t)f * p.cout + c) * p.H + y) * p.W + x] = sg;
+              }
+            }
+          }
+        } else {
+          rowpix[tid] = valid ? ((f * p.H + y) * p.W + x) : -1;
+          uint8_t* srow = staging + (size_t)tid * C::STAGE_PITCH;
+#pragma unroll
+          for (int c0 = 0; c0 < NB; c0 += 32) {
+            float vals[32];
+            tmem_ld32(acc + mb * NB + c0, vals);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(vals[q * 8 + 0], vals[q * 8 + 1]);
+              o.y = pack_bf16x2(vals[q * 8 + 2], vals[q * 8 + 3]);
+              o.z = pack_bf16x2(vals[q * 8 + 4], vals[q * 8 + 5]);
+              o.w = pack_bf16x2(vals[q * 8 + 6], vals[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(srow + c0 * 2 + q * 16) = o;
+            }
+          }
+          if (mb == C::MBLK - 1) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
+          }
+          named_bar_sync(1, 128);
+          // per-channel statistics of the stored (bf16-rounded) values
+          if (p.stats_partial != nullptr) {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+              const int c = tid + i * 128;
+              if (c < NB) {
+                float a1 = 0.f, a2 = 0.f;
+                for (int r = 0; r < 128; ++r) {
+                  if (rowpix[r] >= 0) {
+                    const float val = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(staging + (size_t)r * C::STAGE_PITCH + c * 2));
+                    a1 += val;
+                    a2 = fmaf(val, val, a2);
+                  }
+                }
+                s1[i] += a1;
+                s2[i] += a2;
+              }
+            }
+          }
+          // coalesced store of the valid rows
+          constexpr int LPR = NB / 8;        // lanes per row (16 B each)
+          constexpr int RPI = 32 / LPR;      // rows per warp instruction
+          const int lrow = lane / LPR, lcol = lane % LPR;
+          const int cbase = nblk * NB + lcol * 8;
+          for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
+            const int r = r0 + lrow;
+            const int pix = rowpix[r];
+            if (pix >= 0 && cbase < p.cout) {
+              const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
+              *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
+            }
+          }
+          named_bar_sync(1, 128);
+        }
+      }
+      if constexpr (EPI == SRVP_EPI_RAW_BF16) {
+        if (p.stats_partial != nullptr) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            const int c = tid + i * 128;
+            const int cg = nblk * NB + c;
+            if (c < NB && cg < p.cout) {
+              float* dst = p.stats_partial + ((size_t)mtile * p.cout + cg) * 2;
+              dst[0] = s1[i];
+              dst[1] = s2[i];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// Weight packing: one thread per 8 packed elements.
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpack, int n_real, int n_padded, int k_real,
+                                    int k_padded, long long stride_n, long long stride_k, int flip, int NB, int KCH) {
+  const long long total = (long long)n_padded * k_padded * 9 / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  // idx -> (nblk, stage, tap, chunk j, n)
+  long long t = idx;
+  const int n = (int)(t % NB); t /= NB;
+  const int j = (int)(t % KCH); t /= KCH;
+  const int tap = (int)(t % 9); t /= 9;
+  const int nstages = k_padded / (KCH * 8);
+  const int stage = (int)(t % nstages); t /= nstages;
+  const int nblk = (int)t;
+  const int ng = nblk * NB + n;
+  const int k0 = (stage * KCH + j) * 8;
+  const int te = flip ? 8 - tap : tap;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    v[e] = (ng < n_real && k < k_real) ? w[(long long)ng * stride_n + (long long)k * stride_k + te] : 0.f;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(wpack)[idx] = o;
+}
+
+struct Choice { int NB, MT; };
+Choice choose(int cout_padded) {
+  if (cout_padded <= 16) return {16, 256};
+  if (cout_padded == 64) return {64, 512};
+  if (cout_padded % 256 == 0) return {256, 128};
+  if (cout_padded % 128 == 0) return {128, 256};
+  return {64, 512};
+}
+
+template <int NB, int MT, int KCH, int TPS, int EPI>
+int launch(const ConvDev& d, cudaStream_t stream, int num_sms) {
+  using C = Cfg<NB, MT, KCH, TPS, EPI>;
+  size_t smem = C::smem_bytes(d.P);
+  if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM is allocated for a single resident CTA)
+  SRVP_REQUIRE(smem <= 227 * 1024, "conv3x3: shared memory %zu B exceeds 227 KB (W=%d)", smem, d.W);
+  auto kern = conv3x3_kernel<NB, MT, KCH, TPS, EPI>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    SRVP_REQUIRE(e == cudaSuccess, "conv3x3: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int total = d.num_mtiles * d.num_nblk;
+  const int grid = total < num_sms ? total : num_sms;
+  kern<<<grid, kThreads, smem, stream>>>(d);
+  return check_launch("conv3x3");
+}
+
+}  // namespace
+
+int num_sms_cached();
+
+}  // namespace srvp
+
+using namespace srvp;
+
+extern "C" int srvp_conv3x3_nblock(int32_t cout_padded) { return choose(cout_padded).NB; }
+
+extern "C" int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kchannels_per_stage) {
+  (void)kchannels_per_stage;
+  const Choice c = choose(cout_padded);
+  const long long vtotal = (long long)frames * (H + 1) * (W + 2);
+  return (int)((vtotal + c.MT - 1) / c.MT);
+}
+
+extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRVP_REQUIRE(a != nullptr, "conv3x3: null args");
+  SRVP_REQUIRE(a->nsrc == 1 || a->nsrc == 2, "conv3x3: nsrc must be 1 or 2");
+  const Choice ch = choose(a->cout_padded);
+  SRVP_REQUIRE(a->cout_padded % ch.NB == 0 && a->cout <= a->cout_padded, "conv3x3: bad cout %d / padded %d", a->cout, a->cout_padded);
+  const int kper = (a->src[0].channels == 16 && a->nsrc == 1) ? 16 : 64;
+  ConvDev d{};
+  d.nsrc = a->nsrc;
+  int nst = 0;
+  for (int i = 0; i < a->nsrc; ++i) {
+    const srvp_conv_src& s = a->src[i];
+    SRVP_REQUIRE(s.ptr != nullptr, "conv3x3: src %d null", i);
+    SRVP_REQUIRE(s.channels % kper == 0, "conv3x3: src %d channels %d not a multiple of %d", i, s.channels, kper);
+    SRVP_REQUIRE(s.cpitch % 8 == 0 && s.coff % 8 == 0, "conv3x3: src %d pitch/offset must be multiples of 8", i);
+    SRVP_REQUIRE((s.scale == nullptr) == (s.shift == nullptr), "conv3x3: scale and shift must both be given");
+    if (s.mode == SRVP_SRC_UP2) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "conv3x3: UP2 needs even output size");
+    d.src[i] = SrcDev{reinterpret_cast<const __nv_bfloat16*>(s.ptr), s.scale, s.shift, s.frame_map, s.channels, s.cpitch, s.coff, s.mode, s.lrelu};
+    if (i == 0) d.stages0 = s.channels / kper;
+    nst += s.channels / kper;
+  }
+  d.nstages = nst;
+  d.wpack = reinterpret_cast<const __nv_bfloat16*>(a->wpack);
+  d.F = a->frames; d.H = a->H; d.W = a->W; d.Hp = a->H + 1; d.Wp = a->W + 2;
+  d.vtotal = (long long)d.F * d.Hp * d.Wp;
+  d.cout = a->cout;
+  d.num_nblk = a->cout_padded / ch.NB;
+  d.num_mtiles = (int)((d.vtotal + ch.MT - 1) / ch.MT);
+  d.P = ch.MT + 2 * d.Wp + 2;
+  d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  d.out_cpitch = a->out_cpitch; d.out_coff = a->out_coff;
+  d.stats_partial = a->stats_partial;
+  d.out_f32 = a->out_f32_nchw;
+  const int sms = num_sms_cached();
+  if (a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32) {
+    SRVP_REQUIRE(ch.NB == 16 && kper == 64 && a->out_f32_nchw != nullptr, "conv3x3: sigmoid epilogue needs cout<=16, 64-channel stages");
+    return launch<16, 256, 8, 1, SRVP_EPI_SIGMOID_NCHW_F32>(d, stream, sms);
+  }
+  SRVP_REQUIRE(a->out != nullptr && a->out_cpitch % 8 == 0 && a->out_coff % 8 == 0, "conv3x3: bad output tensor");
+  if (kper == 16) {
+    SRVP_REQUIRE(ch.NB == 64, "conv3x3: thin-input variant only built for 64 output channels");
+    return launch<64, 512, 2, 9, SRVP_EPI_RAW_BF16>(d, stream, sms);
+  }
+  switch (ch.NB) {
+    case 64: return launch<64, 512, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
+    case 128: return launch<128, 256, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
+    case 256: return launch<256, 128, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
+    default: break;
+  }
+  SRVP_REQUIRE(false, "conv3x3: unsupported cout_padded %d", a->cout_padded);
+}
+
+extern "C" int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32_t n_real, int32_t n_padded, int32_t k_real, int32_t k_padded,
+                                         int64_t stride_n, int64_t stride_k, int32_t flip, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const Choice ch = choose(n_padded);
+  SRVP_REQUIRE(n_padded % ch.NB == 0, "pack: n_padded %d not a multiple of block %d", n_padded, ch.NB);
+  const int KCH = (k_padded == 16) ? 2 : 8;
+  SRVP_REQUIRE(k_padded % (KCH * 8) == 0, "pack: k_padded %d", k_padded);
+  const long long total = (long long)n_padded * k_padded * 9 / 8;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  pack_conv3x3_kernel<<<(unsigned)blocks, threads, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wpack), n_real, n_padded, k_real, k_padded,
+                                                                stride_n, stride_k, flip, ch.NB, KCH);
+  return check_launch("pack_conv3x3");
+}
