@@ -78,6 +78,25 @@ int srvp_conv3x3(const srvp_conv3x3_args* args, void* stream);
 int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32_t n_real, int32_t n_padded, int32_t k_real,
                               int32_t k_padded, int64_t stride_n, int64_t stride_k, int32_t flip, void* stream);
 
+/* Weight gradient of the same convolutions (autograd of module/conv.py:198-220, :333-354 via train.py:119):
+ * dw[co*stride_cout + ci*stride_cin + (flip ? 8-tap : tap)] += sum_p dz[p, co] * a[p + tap offset, ci], where `a` is
+ * recomputed by the loader from the fused activation sources (same semantics as srvp_conv3x3's sources).
+ * nn.Conv2d weight (Cout,Cin,3,3): stride_cout = Cin*9, stride_cin = 9, flip = 0;
+ * nn.ConvTranspose2d weight (Cin,Cout,3,3): stride_cout = 9, stride_cin = Cout*9, flip = 1. dw is ACCUMULATED into. */
+typedef struct {
+  srvp_conv_src act[2];
+  int32_t nact;
+  const srvp_bf16* dz;  /* NHWC bf16 gradient w.r.t. the raw conv output */
+  int32_t dz_channels;  /* channels to read (padded count, multiple of 8) */
+  int32_t dz_cpitch, dz_coff;
+  int32_t frames, H, W;
+  int32_t cout, cin;    /* real channel counts (padded channels are not written) */
+  float* dw;
+  int64_t stride_cout, stride_cin;
+  int32_t flip;
+} srvp_wgrad3x3_args;
+int srvp_wgrad3x3(const srvp_wgrad3x3_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,12 @@ class Conv3x3Args(ctypes.Structure):
                 ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr)]
 
 
+class Wgrad3x3Args(ctypes.Structure):
+    _fields_ = [('act', ConvSrc * 2), ('nact', c_int), ('dz', c_ptr), ('dz_channels', c_int), ('dz_cpitch', c_int),
+                ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
+                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int)]
+
+
 SRC_DIRECT, SRC_POOL2, SRC_UP2 = 0, 1, 2
 EPI_RAW_BF16, EPI_SIGMOID_NCHW_F32 = 0, 1
 
@@ -51,7 +57,7 @@ def lib():
 # every symbol declared in include/srvp_b200.h
 EXPORTS = [
     'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
-    'srvp_pack_conv3x3_weights',
+    'srvp_pack_conv3x3_weights', 'srvp_wgrad3x3',
 ]
 
 

@@ -21,6 +21,7 @@
 // activation loaders, warp 8 MMA issuer (one thread), warp 9 weight TMA-bulk issuer (one thread).
 // TMEM: 2 accumulator stages x (MT/128) x NB fp32 columns, so the epilogue of tile i overlaps tile i+1.
 #include "common.cuh"
+#include "conv_common.cuh"
 #include "../../include/srvp_b200.h"
 
 namespace srvp {
@@ -29,14 +30,6 @@ namespace {
 
 constexpr int kThreads = 320;
 constexpr int kHaloStages = 2;
-
-struct SrcDev {
-  const __nv_bfloat16* ptr;
-  const float* scale;
-  const float* shift;
-  const int* frame_map;
-  int channels, cpitch, coff, mode, lrelu;
-};
 
 struct ConvDev {
   SrcDev src[2];
@@ -53,38 +46,6 @@ struct ConvDev {
   float* stats_partial;
   float* out_f32;
 };
-
-__device__ __forceinline__ uint4 transform8(uint4 raw, const float* __restrict__ scale, const float* __restrict__ shift, int lrelu_flag) {
-  if (scale == nullptr && !lrelu_flag) return raw;
-  float v[8];
-  {
-    float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y), c = unpack_bf16x2(raw.z), d = unpack_bf16x2(raw.w);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-  }
-  if (scale != nullptr) {
-    float4 s0 = __ldg(reinterpret_cast<const float4*>(scale)), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 1);
-    float4 h0 = __ldg(reinterpret_cast<const float4*>(shift)), h1 = __ldg(reinterpret_cast<const float4*>(shift) + 1);
-    v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-    v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-  }
-  if (lrelu_flag) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = lrelu(v[i]);
-  }
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-  return o;
-}
-
-__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
-  uint4 o;
-  __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
-  __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&b);
-  __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) po[i] = __hmax2(pa[i], pb[i]);
-  return o;
-}
 
 template <int NB, int MT, int KCH, int TPS, int EPI>
 struct Cfg {

@@ -67,6 +67,39 @@ def pack_conv3x3(weight, kind, out=None):
     return out
 
 
+def _fill_src(cs, s):
+    assert s.tensor.dtype == torch.bfloat16
+    cs.ptr = ptr(s.tensor)
+    cs.scale = ptr(s.scale)
+    cs.shift = ptr(s.shift)
+    cs.frame_map = ptr(s.frame_map)
+    cs.channels = s.channels
+    cs.cpitch = s.tensor.shape[-1]
+    cs.coff = s.coff
+    cs.mode = s.mode
+    cs.lrelu = int(s.lrelu)
+
+
+def wgrad3x3(srcs, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0):
+    """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'."""
+    a = _lib.Wgrad3x3Args()
+    a.nact = len(srcs)
+    for i, s in enumerate(srcs):
+        _fill_src(a.act[i], s)
+    assert dz.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    a.dz = ptr(dz)
+    a.dz_channels, a.dz_cpitch, a.dz_coff = dz_channels, dz.shape[-1], dz_coff
+    a.frames, a.H, a.W = frames, H, W
+    a.cout, a.cin = cout, cin
+    a.dw = ptr(dw)
+    if kind == 'conv':
+        a.stride_cout, a.stride_cin, a.flip = cin * 9, 9, 0
+    else:
+        a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
+    check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
+    return dw
+
+
 def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False):
     """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None)."""
     a = _lib.Conv3x3Args()
