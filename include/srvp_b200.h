@@ -97,6 +97,89 @@ typedef struct {
 } srvp_wgrad3x3_args;
 int srvp_wgrad3x3(const srvp_wgrad3x3_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Layout conversion at the API boundary (the reference API is (T,B,C,H,W) fp32; kernels use NHWC bf16).
+ * Replaces x.view(nt*bsz, ...) feeding nn.Conv2d (module/srvp.py:176-178) and the x_flat.view of :226.
+ * ---------------------------------------------------------------------------------------------- */
+int srvp_nchw_f32_to_nhwc_bf16(const float* x, srvp_bf16* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpad, void* stream);
+int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpitch, void* stream);
+/* Materialises a fused source (BN apply, LeakyReLU, pool/upsample, frame gather) as dense NHWC bf16 (frames,H,W,channels). */
+int srvp_materialize_src(const srvp_conv_src* src, srvp_bf16* out, int32_t frames, int32_t H, int32_t W, void* stream);
+/* out[a][c][b] = in[a][b][c]; used to view 4x4 (de)conv weights as GEMM operands (module/conv.py:224, :330). */
+int srvp_transpose_last2_f32(const float* in, float* out, int32_t A, int32_t B, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm2d (module/conv.py:103-104; semantics SURVEY.md App. C).
+ * Forward: the conv / GEMM epilogue (or srvp_channel_stats) produces per-tile (sum, sumsq); srvp_bn_finalize reduces
+ * them in fp64 over `rows` tiles, writes the affine (scale = gamma*invstd, shift = beta - mean*scale), the saved
+ * (mean, invstd), and updates running stats (momentum, unbiased variance) when they are given.
+ * ---------------------------------------------------------------------------------------------- */
+int srvp_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                     void* stream);
+int srvp_bn_eval_params(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* scale,
+                        float* shift, int32_t C, void* stream);
+int srvp_channel_stats_rows(int64_t rows);
+int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, float* partial /* [srvp_channel_stats_rows(rows)][C][2] */, void* stream);
+
+/* Backward of conv -> BN(train) -> LeakyReLU [-> MaxPool2d(2) | Upsample(2)] (autograd of conv.py:101-107, :204, :331).
+ * reduce:   g = lrelu'(bn(z)) * (da routed through pool/upsample + skip-connection gradient), partial sums of (g, g*xhat)
+ * finalize: c1 = mean(g), c2 = mean(g*xhat); dgamma += sum(g*xhat); dbeta += sum(g)
+ * apply:    dz = gamma*invstd*(g - c1 - xhat*c2), in place on g. */
+typedef struct {
+  const srvp_bf16* z;     /* raw conv output of this layer (frames,H,W,C) */
+  const float* scale;     /* forward affine of this layer */
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const srvp_bf16* da;    /* gradient w.r.t. what the consumer read: DIRECT (frames,H,W), POOL2 (frames,H/2,W/2), UP2 (frames,2H,2W) */
+  int32_t da_cpitch, da_coff, da_mode;
+  const srvp_bf16* skip;  /* optional: gradient from the decoder's skip input (nt*B, H, W, skip_cpitch), summed over nt */
+  int32_t skip_cpitch, skip_coff, nt, B;
+  const int32_t* inv_map; /* (frames): video index b if this frame was selected as skip frame (srvp.py:185-187), else -1 */
+  srvp_bf16* g;           /* out (frames,H,W,C) */
+  float* partial;         /* out [srvp_bn_bwd_reduce_rows(...)][C][2] */
+  int32_t frames, H, W, C;
+  int32_t lrelu;
+} srvp_bn_bwd_args;
+int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t da_mode);
+int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* args, void* stream);
+int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,
+                         void* stream);
+int srvp_bn_bwd_apply(srvp_bf16* g_inout, const srvp_bf16* z, const float* gamma, const float* mean, const float* invstd, const float* c1,
+                      const float* c2, int64_t positions, int32_t C, void* stream);
+/* encoder.last_conv's BatchNorm2d + Tanh on a (rows = T*B, C = nhx) fp32 matrix (conv.py:179, :221-224), forward and backward.
+ * training != 0: batch statistics (saved to mean/invstd, affine written to scale/shift, running stats updated when given);
+ * training == 0: scale/shift are inputs (srvp_bn_eval_params). */
+int srvp_bn_tanh_rows_fwd(const float* z, int32_t rows, int32_t C, const float* gamma, const float* beta, float eps, float momentum,
+                          float* running_mean, float* running_var, int32_t training, float* scale, float* shift, float* mean, float* invstd,
+                          float* out, void* stream);
+int srvp_bn_tanh_rows_bwd(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* gamma, const float* mean,
+                          const float* invstd, float* dz, float* dgamma, float* dbeta, void* stream);
+/* Backward of torch.sigmoid on the decoder output (conv.py:273-274): dz(frames,H,W,16) = dxhat * xhat * (1 - xhat), NCHW fp32 in. */
+int srvp_sigmoid_bwd_nchw_to_nhwc16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense GEMM on tcgen05: C[m,n] (+)= act(sum_k A[m,k]*B[n,k] + bias). Element strides; each operand needs one unit stride.
+ * Replaces nn.Linear (module/srvp.py:127-133, mlp.py:43), encoder.last_conv / decoder.first_upconv (conv.py:224, :330)
+ * and their gradients.
+ * ---------------------------------------------------------------------------------------------- */
+enum { SRVP_F32 = 0, SRVP_BF16 = 1 };
+enum { SRVP_ACT_NONE = 0, SRVP_ACT_RELU = 1, SRVP_ACT_TANH = 2 };
+typedef struct {
+  const void* a; int32_t a_dtype; int64_t a_sm, a_sk;
+  const void* b; int32_t b_dtype; int64_t b_sn, b_sk;
+  void* c; int32_t c_dtype; int64_t c_sm, c_sn;
+  const float* bias;   /* optional, indexed by n (or by m when bias_on_m) */
+  int32_t bias_on_m;
+  int32_t M, N, K;
+  int32_t act;         /* SRVP_ACT_* */
+  int32_t accumulate;  /* C += result (fp32 C only) */
+  int32_t split_k;     /* 0 = automatic (only splits accumulate-mode problems) */
+} srvp_gemm_args;
+int srvp_gemm(const srvp_gemm_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,22 @@ class Wgrad3x3Args(ctypes.Structure):
                 ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int)]
 
 
+class BnBwdArgs(ctypes.Structure):
+    _fields_ = [('z', c_ptr), ('scale', c_ptr), ('shift', c_ptr), ('mean', c_ptr), ('invstd', c_ptr), ('da', c_ptr),
+                ('da_cpitch', c_int), ('da_coff', c_int), ('da_mode', c_int), ('skip', c_ptr), ('skip_cpitch', c_int),
+                ('skip_coff', c_int), ('nt', c_int), ('B', c_int), ('inv_map', c_ptr), ('g', c_ptr), ('partial', c_ptr),
+                ('frames', c_int), ('H', c_int), ('W', c_int), ('C', c_int), ('lrelu', c_int)]
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [('a', c_ptr), ('a_dtype', c_int), ('a_sm', c_i64), ('a_sk', c_i64), ('b', c_ptr), ('b_dtype', c_int),
+                ('b_sn', c_i64), ('b_sk', c_i64), ('c', c_ptr), ('c_dtype', c_int), ('c_sm', c_i64), ('c_sn', c_i64),
+                ('bias', c_ptr), ('bias_on_m', c_int), ('M', c_int), ('N', c_int), ('K', c_int), ('act', c_int),
+                ('accumulate', c_int), ('split_k', c_int)]
+
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 SRC_DIRECT, SRC_POOL2, SRC_UP2 = 0, 1, 2
 EPI_RAW_BF16, EPI_SIGMOID_NCHW_F32 = 0, 1
 
@@ -57,7 +73,10 @@ def lib():
 # every symbol declared in include/srvp_b200.h
 EXPORTS = [
     'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
-    'srvp_pack_conv3x3_weights', 'srvp_wgrad3x3',
+    'srvp_pack_conv3x3_weights', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16', 'srvp_nhwc_bf16_to_nchw_f32',
+    'srvp_materialize_src', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
+    'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
+    'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd',
 ]
 
 

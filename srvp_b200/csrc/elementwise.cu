@@ -1,0 +1,580 @@
+// HBM-bound kernels around the convolutions: layout conversion, batch-norm statistics finalisation,
+// batch-norm / LeakyReLU / max-pool / upsample backward, sigmoid backward.
+//
+// Reference semantics (module/conv.py:101-107 conv -> BatchNorm2d -> LeakyReLU(0.2)):
+//   train: mean / biased variance over all N*H*W positions of the flattened T*B batch, eps 1e-5, running stats
+//   updated with momentum 0.1 and the unbiased variance; eval: running stats.
+// All kernels use 128-bit accesses (8 bf16 channels per thread) on NHWC tensors and warp/block reductions.
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "../../include/srvp_b200.h"
+
+namespace srvp {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long npix_total, int C, int HW, int Cpad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over (f, y, x)
+  if (i >= npix_total) return;
+  const long long f = i / HW;
+  const int p = (int)(i - f * HW);
+  const float* src = x + f * C * HW + p;
+  __nv_bfloat16* dst = out + i * Cpad;
+  for (int c0 = 0; c0 < Cpad; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (c0 + e < C) ? __ldg(src + (long long)(c0 + e) * HW) : 0.f;
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + c0) = o;
+  }
+}
+
+// NHWC bf16 (pitch Cp) -> NCHW fp32, C real channels. One thread per (f, c, pixel); coalesced on the write side.
+__global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long total, int C, int HW, int Cp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = (int)(i % HW);
+  const long long fc = i / HW;
+  const int c = (int)(fc % C);
+  const long long f = fc / C;
+  out[i] = __bfloat162float(in[(f * HW + p) * Cp + c]);
+}
+
+// Materialises a fused source (BN apply + LeakyReLU + pool/upsample + frame gather) as NHWC bf16.
+__global__ void materialize_src_kernel(const SrcDev sd, __nv_bfloat16* __restrict__ out, long long total_chunks, int H, int W, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int cpp = C / 8;
+  const int j = (int)(i % cpp);
+  long long pix = i / cpp;
+  const int x = (int)(pix % W); pix /= W;
+  const int y = (int)(pix % H);
+  const int f = (int)(pix / H);
+  const uint4 v = load_src8(sd, f, y, x, H, W, j * 8);
+  *reinterpret_cast<uint4*>(out + (i * 8)) = v;
+}
+
+// ------------------------------------------------------------------------------------------------ BN forward stats
+// One warp per channel reduces the per-tile partial sums in fp64, then derives the affine and updates running stats.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = lane; r < rows; r += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
+    s1 += v.x;
+    s2 += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = invstd;
+    if (running_mean != nullptr) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+__global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                                      const float* __restrict__ rv, float eps, float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(rv[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+// Per-channel (sum, sumsq) partials of a [rows, C] bf16 matrix (used for GEMM-produced layers). Block = C threads.
+__global__ void channel_stats_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int C, int rows_per_block, float* __restrict__ partial) {
+  const int c = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s1 = 0.f, s2 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float v = __bfloat162float(z[r * C + c]);
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+  partial[((size_t)blockIdx.x * C + c) * 2 + 0] = s1;
+  partial[((size_t)blockIdx.x * C + c) * 2 + 1] = s2;
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward
+struct BnBwdDev {
+  const __nv_bfloat16* z;      // raw conv output of this layer [F,H,W,C]
+  const float* scale;          // forward affine: y = z*scale + shift
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const __nv_bfloat16* da;     // gradient w.r.t. the activated output as consumed downstream
+  int da_cpitch, da_coff, da_mode;  // DIRECT: [F,H,W]; POOL2: [F,H/2,W/2] (route to arg-max); UP2: [F,2H,2W] (sum of 4)
+  const __nv_bfloat16* skip;   // optional gradient of the skip-connection consumer [nt*B, H, W, skip_cpitch]
+  int skip_cpitch, skip_coff, nt, B;
+  const int* inv_map;          // [F]: video index if this frame feeds the skip connection, else -1
+  __nv_bfloat16* g;            // out: gradient w.r.t. the BN output (before the BN backward correction) [F,H,W,C]
+  float* partial;              // out: [gridDim.x][C][2] = (sum g, sum g*xhat)
+  int F, H, W, C;
+  int lrelu;
+};
+
+__device__ __forceinline__ void unpack8(uint4 r, float* v) {
+  float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+// Work item = one 2x2 window (POOL2) or one pixel (otherwise) x 8 channels. Threads of a block share the channel chunk
+// index pattern tid % (C/8), so per-thread register sums are per-channel; they are combined across the block in smem.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdDev p, long long items, int items_per_block) {
+  __shared__ float red[256 * 17];
+  const int cpp = p.C / 8;               // chunks per pixel
+  const int tid = threadIdx.x;
+  const int j = tid % cpp;               // this thread's channel chunk
+  const int lanes = 256 / cpp;           // pixel lanes per block
+  const int pl = tid / cpp;
+  const int c0 = j * 8;
+  float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = p.scale[c0 + e]; sh[e] = p.shift[c0 + e]; mu[e] = p.mean[c0 + e]; is[e] = p.invstd[c0 + e]; }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+  const bool pooled = p.da_mode == SRVP_SRC_POOL2;
+  const int Hi = pooled ? p.H / 2 : p.H, Wi = pooled ? p.W / 2 : p.W;  // item grid
+  const long long i0 = (long long)blockIdx.x * items_per_block;
+  const long long i1 = min(items, i0 + items_per_block);
+  if (pl < lanes) {
+    for (long long it = i0 + pl; it < i1; it += lanes) {
+      const int xi = (int)(it % Wi);
+      const long long t2 = it / Wi;
+      const int yi = (int)(t2 % Hi);
+      const int f = (int)(t2 / Hi);
+      const int b = p.inv_map ? __ldg(p.inv_map + f) : -1;
+      if (pooled) {
+        float da[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.da + (((size_t)f * Hi + yi) * Wi + xi) * p.da_cpitch + p.da_coff + c0)), da);
+        float zv[4][8], yv[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int y = 2 * yi + (q >> 1), x = 2 * xi + (q & 1);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(p.z + (((size_t)f * p.H + y) * p.W + x) * p.C + c0)), zv[q]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = fmaf(zv[q][e], sc[e], sh[e]);
+            if (p.lrelu) v = lrelu(v);
+            yv[q][e] = bf16_round(v);  // the forward max-pool compared bf16-rounded activations
+          }
+        }
+        float gq[4][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int am = 0;
+          float best = yv[0][e];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) if (yv[q][e] > best) { best = yv[q][e]; am = q; }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gq[q][e] = (q == am) ? da[e] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int y = 2 * yi + (q >> 1), x = 2 * xi + (q & 1);
+          if (b >= 0) {
+            for (int t = 0; t < p.nt; ++t) {
+              float sk[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(p.skip + ((((size_t)t * p.B + b) * p.H + y) * p.W + x) * p.skip_cpitch + p.skip_coff + c0)), sk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) gq[q][e] += sk[e];
+            }
+          }
+          float gout[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float pre = fmaf(zv[q][e], sc[e], sh[e]);
+            const float g = gq[q][e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
+            const float gr = bf16_round(g);
+            gout[e] = gr;
+            s1[e] += gr;
+            s2[e] = fmaf(gr, (zv[q][e] - mu[e]) * is[e], s2[e]);
+          }
+          *reinterpret_cast<uint4*>(p.g + (((size_t)f * p.H + y) * p.W + x) * p.C + c0) = pack8(gout);
+        }
+      } else {
+        const int y = yi, x = xi;
+        float zv[8], gsum[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.z + (((size_t)f * p.H + y) * p.W + x) * p.C + c0)), zv);
+        if (p.da_mode == SRVP_SRC_UP2) {
+          const int W2 = p.W * 2;
+          const __nv_bfloat16* base = p.da + (((size_t)f * (p.H * 2) + 2 * y) * W2 + 2 * x) * p.da_cpitch + p.da_coff + c0;
+          float t0[8], t1[8], t2v[8], t3[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base)), t0);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + p.da_cpitch)), t1);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)W2 * p.da_cpitch)), t2v);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)(W2 + 1) * p.da_cpitch)), t3);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gsum[e] = (t0[e] + t1[e]) + (t2v[e] + t3[e]);
+        } else {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(p.da + (((size_t)f * p.H + y) * p.W + x) * p.da_cpitch + p.da_coff + c0)), gsum);
+        }
+        if (b >= 0) {
+          for (int t = 0; t < p.nt; ++t) {
+            float sk[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.skip + ((((size_t)t * p.B + b) * p.H + y) * p.W + x) * p.skip_cpitch + p.skip_coff + c0)), sk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gsum[e] += sk[e];
+          }
+        }
+        float gout[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pre = fmaf(zv[e], sc[e], sh[e]);
+          const float g = gsum[e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
+          const float gr = bf16_round(g);
+          gout[e] = gr;
+          s1[e] += gr;
+          s2[e] = fmaf(gr, (zv[e] - mu[e]) * is[e], s2[e]);
+        }
+        *reinterpret_cast<uint4*>(p.g + (((size_t)f * p.H + y) * p.W + x) * p.C + c0) = pack8(gout);
+      }
+    }
+  }
+  // block reduction over pixel lanes (fixed order -> deterministic)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[tid * 17 + e] = s1[e]; red[tid * 17 + 8 + e] = s2[e]; }
+  __syncthreads();
+  if (tid < cpp) {
+    float a1[8], a2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float* r = red + (l * cpp + tid) * 17;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a1[e] += r[e]; a2[e] += r[8 + e]; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float* dst = p.partial + ((size_t)blockIdx.x * p.C + tid * 8 + e) * 2;
+      dst[0] = a1[e];
+      dst[1] = a2[e];
+    }
+  }
+}
+
+// c1 = sum(g)/n, c2 = sum(g*xhat)/n; dgamma += sum(g*xhat), dbeta += sum(g). One warp per channel.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float* __restrict__ c1, float* __restrict__ c2,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = lane; r < rows; r += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
+    s1 += v.x;
+    s2 += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    c1[c] = (float)(s1 / count);
+    c2[c] = (float)(s2 / count);
+    if (dgamma != nullptr) dgamma[c] += (float)s2;
+    if (dbeta != nullptr) dbeta[c] += (float)s1;
+  }
+}
+
+// dz = gamma*invstd * (g - c1 - xhat*c2), in place on g.
+__global__ void bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ z, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ c1,
+                                    const float* __restrict__ c2, long long total_chunks, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_chunks) return;
+  const int c0 = (int)(i % (C / 8)) * 8;
+  float gv[8], zv[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(z + i * 8)), zv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float is = __ldg(invstd + c0 + e);
+    const float xh = (zv[e] - __ldg(mean + c0 + e)) * is;
+    o[e] = __ldg(gamma + c0 + e) * is * (gv[e] - __ldg(c1 + c0 + e) - xh * __ldg(c2 + c0 + e));
+  }
+  *reinterpret_cast<uint4*>(g + i * 8) = pack8(o);
+}
+
+// dz16[f,y,x,c] = dxhat[f,c,y,x] * xhat * (1 - xhat) for c < C, zero padding up to 16 channels.
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ xh, __nv_bfloat16* __restrict__ out, long long npix, int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const long long f = i / HW;
+  const int pp = (int)(i - f * HW);
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    if (c < C) {
+      const long long idx = (f * C + c) * HW + pp;
+      const float s = __ldg(xh + idx);
+      v[c] = __ldg(dx + idx) * s * (1.f - s);
+    } else {
+      v[c] = 0.f;
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+  dst[0] = pack8(v);
+  dst[1] = pack8(v + 8);
+}
+
+// out[a][c][b] = in[a][b][c]  (batched transpose of the two trailing dims), fp32.
+__global__ void transpose_last2_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int Bd, int Cd) {
+  __shared__ float tile[32][33];
+  const int a = blockIdx.z;
+  const int b0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int b = b0 + i, c = c0 + threadIdx.x;
+    if (b < Bd && c < Cd) tile[i][threadIdx.x] = in[((size_t)a * Bd + b) * Cd + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, b = b0 + threadIdx.x;
+    if (b < Bd && c < Cd) out[((size_t)a * Cd + c) * Bd + b] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN + tanh on [rows, C] fp32
+// encoder.last_conv's BatchNorm2d + Tanh (module/conv.py:179 / :221-224) acts on a (T*B, nhx, 1, 1) tensor: one block per
+// channel, fp64 statistics. Training: batch stats (+ running update); eval: the affine is given.
+__global__ void __launch_bounds__(256) bn_tanh_rows_fwd_kernel(const float* __restrict__ z, int rows, int C, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rm,
+                                                                 float* __restrict__ rv, int training, float* __restrict__ scale,
+                                                                 float* __restrict__ shift, float* __restrict__ mean_out,
+                                                                 float* __restrict__ invstd_out, float* __restrict__ out) {
+  __shared__ double r1[256], r2[256];
+  __shared__ float s_sc, s_sh;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  if (training) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = tid; r < rows; r += 256) {
+      const double v = z[(size_t)r * C + c];
+      s1 += v;
+      s2 += v * v;
+    }
+    r1[tid] = s1; r2[tid] = s2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) { r1[tid] += r1[tid + o]; r2[tid] += r2[tid + o]; }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const double mean = r1[0] / rows;
+      double var = r2[0] / rows - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      s_sc = gamma[c] * invstd;
+      s_sh = beta[c] - (float)mean * s_sc;
+      scale[c] = s_sc; shift[c] = s_sh; mean_out[c] = (float)mean; invstd_out[c] = invstd;
+      if (rm != nullptr) {
+        const double unbiased = rows > 1 ? var * rows / (rows - 1.0) : var;
+        rm[c] = (1.f - momentum) * rm[c] + momentum * (float)mean;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+      }
+    }
+  } else if (tid == 0) {
+    s_sc = scale[c];
+    s_sh = shift[c];
+  }
+  __syncthreads();
+  const float sc = s_sc, sh = s_sh;
+  for (int r = tid; r < rows; r += 256) out[(size_t)r * C + c] = tanhf(fmaf(z[(size_t)r * C + c], sc, sh));
+}
+
+__global__ void __launch_bounds__(256) bn_tanh_rows_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ z,
+                                                                 int rows, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd, float* __restrict__ dz, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta) {
+  __shared__ double r1[256], r2[256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const float mu = mean[c], is = invstd[c];
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = tid; r < rows; r += 256) {
+    const float o = out[(size_t)r * C + c];
+    const float g = dout[(size_t)r * C + c] * (1.f - o * o);
+    s1 += g;
+    s2 += (double)g * ((z[(size_t)r * C + c] - mu) * is);
+  }
+  r1[tid] = s1; r2[tid] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { r1[tid] += r1[tid + o]; r2[tid] += r2[tid + o]; }
+    __syncthreads();
+  }
+  const float c1 = (float)(r1[0] / rows), c2 = (float)(r2[0] / rows);
+  if (tid == 0) {
+    dgamma[c] += (float)r2[0];
+    dbeta[c] += (float)r1[0];
+  }
+  const float k = gamma[c] * is;
+  for (int r = tid; r < rows; r += 256) {
+    const float o = out[(size_t)r * C + c];
+    const float g = dout[(size_t)r * C + c] * (1.f - o * o);
+    const float xh = (z[(size_t)r * C + c] - mu) * is;
+    dz[(size_t)r * C + c] = k * (g - c1 - xh * c2);
+  }
+}
+
+inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+}  // namespace srvp
+
+using namespace srvp;
+
+extern "C" int srvp_nchw_f32_to_nhwc_bf16(const float* x, srvp_bf16* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpad,
+                                          void* stream) {
+  SRVP_REQUIRE(cpad % 8 == 0 && cpad >= C, "nchw_to_nhwc: bad channel padding %d for %d", cpad, C);
+  const long long npix = (long long)frames * H * W;
+  nchw_to_nhwc_bf16_kernel<<<blocks_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), npix, C, H * W, cpad);
+  return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpitch,
+                                          void* stream) {
+  const long long total = (long long)frames * C * H * W;
+  nhwc_bf16_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, total, C, H * W, cpitch);
+  return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int srvp_materialize_src(const srvp_conv_src* s, srvp_bf16* out, int32_t frames, int32_t H, int32_t W, void* stream) {
+  SRVP_REQUIRE(s != nullptr && s->channels % 8 == 0, "materialize_src: bad source");
+  SrcDev sd{reinterpret_cast<const __nv_bfloat16*>(s->ptr), s->scale, s->shift, s->frame_map, s->channels, s->cpitch, s->coff, s->mode, s->lrelu};
+  const long long total = (long long)frames * H * W * (s->channels / 8);
+  materialize_src_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(sd, reinterpret_cast<__nv_bfloat16*>(out), total, H, W, s->channels);
+  return check_launch("materialize_src");
+}
+
+extern "C" int srvp_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                void* stream) {
+  SRVP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must both be given or both be NULL");
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                                                                    shift, mean, invstd);
+  return check_launch("bn_finalize");
+}
+
+extern "C" int srvp_bn_eval_params(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* scale,
+                                   float* shift, int32_t C, void* stream) {
+  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
+  return check_launch("bn_eval_params");
+}
+
+extern "C" int srvp_channel_stats_rows(int64_t rows) { return (int)((rows + 255) / 256); }
+
+extern "C" int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, float* partial, void* stream) {
+  SRVP_REQUIRE(C <= 1024, "channel_stats: C=%d too large", C);
+  const int nb = (int)((rows + 255) / 256);
+  channel_stats_kernel<<<nb, C, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(z), rows, C, 256, partial);
+  return check_launch("channel_stats");
+}
+
+static int bn_bwd_blocks(long long items) {
+  long long nb = (items + 2047) / 2048;
+  if (nb > 4096) nb = 4096;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+extern "C" int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t da_mode) {
+  const long long items = (da_mode == SRVP_SRC_POOL2) ? (long long)frames * (H / 2) * (W / 2) : (long long)frames * H * W;
+  return bn_bwd_blocks(items);
+}
+
+extern "C" int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* a, void* stream) {
+  SRVP_REQUIRE(a != nullptr && a->z && a->da && a->g && a->partial, "bn_bwd_reduce: null argument");
+  SRVP_REQUIRE(a->C % 8 == 0 && a->C <= 2048 && 256 % (a->C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", a->C);
+  BnBwdDev d{};
+  d.z = reinterpret_cast<const __nv_bfloat16*>(a->z);
+  d.scale = a->scale; d.shift = a->shift; d.mean = a->mean; d.invstd = a->invstd;
+  d.da = reinterpret_cast<const __nv_bfloat16*>(a->da);
+  d.da_cpitch = a->da_cpitch; d.da_coff = a->da_coff; d.da_mode = a->da_mode;
+  d.skip = reinterpret_cast<const __nv_bfloat16*>(a->skip);
+  d.skip_cpitch = a->skip_cpitch; d.skip_coff = a->skip_coff; d.nt = a->nt; d.B = a->B;
+  d.inv_map = a->skip ? a->inv_map : nullptr;
+  d.g = reinterpret_cast<__nv_bfloat16*>(a->g);
+  d.partial = a->partial;
+  d.F = a->frames; d.H = a->H; d.W = a->W; d.C = a->C; d.lrelu = a->lrelu;
+  const bool pooled = a->da_mode == SRVP_SRC_POOL2;
+  if (pooled) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "bn_bwd_reduce: pooled mode needs even size");
+  const long long items = pooled ? (long long)a->frames * (a->H / 2) * (a->W / 2) : (long long)a->frames * a->H * a->W;
+  const int nb = bn_bwd_blocks(items);
+  const int ipb = (int)((items + nb - 1) / nb);
+  bn_bwd_reduce_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(d, items, ipb);
+  return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,
+                                    void* stream) {
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, count, c1, c2, dgamma, dbeta);
+  return check_launch("bn_bwd_finalize");
+}
+
+extern "C" int srvp_bn_bwd_apply(srvp_bf16* g, const srvp_bf16* z, const float* gamma, const float* mean, const float* invstd, const float* c1,
+                                 const float* c2, int64_t positions, int32_t C, void* stream) {
+  SRVP_REQUIRE(C % 8 == 0, "bn_bwd_apply: C must be a multiple of 8");
+  const long long total = positions * (C / 8);
+  bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z),
+                                                                                gamma, mean, invstd, c1, c2, total, C);
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int srvp_sigmoid_bwd_nchw_to_nhwc16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,
+                                               void* stream) {
+  SRVP_REQUIRE(C <= 16, "sigmoid_bwd: C=%d > 16", C);
+  const long long npix = (long long)frames * H * W;
+  sigmoid_bwd_kernel<<<blocks_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(dxhat, xhat, reinterpret_cast<__nv_bfloat16*>(dz16), npix, C, H * W);
+  return check_launch("sigmoid_bwd");
+}
+
+extern "C" int srvp_transpose_last2_f32(const float* in, float* out, int32_t A, int32_t B, int32_t C, void* stream) {
+  dim3 grid((C + 31) / 32, (B + 31) / 32, A), block(32, 8);
+  SRVP_REQUIRE(A <= 65535 && grid.y <= 65535, "transpose_last2: dims too large");
+  transpose_last2_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, A, B, C);
+  return check_launch("transpose_last2");
+}
+
+extern "C" int srvp_bn_tanh_rows_fwd(const float* z, int32_t rows, int32_t C, const float* gamma, const float* beta, float eps, float momentum,
+                                     float* running_mean, float* running_var, int32_t training, float* scale, float* shift, float* mean, float* invstd,
+                                     float* out, void* stream) {
+  bn_tanh_rows_fwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(z, rows, C, gamma, beta, eps, momentum, running_mean, running_var, training, scale, shift,
+                                                               mean, invstd, out);
+  return check_launch("bn_tanh_rows_fwd");
+}
+
+extern "C" int srvp_bn_tanh_rows_bwd(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* gamma, const float* mean,
+                                     const float* invstd, float* dz, float* dgamma, float* dbeta, void* stream) {
+  bn_tanh_rows_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dout, out, z, rows, C, gamma, mean, invstd, dz, dgamma, dbeta);
+  return check_launch("bn_tanh_rows_bwd");
+}

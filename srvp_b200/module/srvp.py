@@ -1,0 +1,178 @@
+"""B200-native StochasticLatentResidualVideoPredictor with the reference's class surface (module/srvp.py:29-470).
+
+Same constructor signature, attributes, sub-module names (state-dict keys), method names, argument
+meanings, return tuples and train/eval behaviour as the reference class, so `train.py` / `test.py` written against the
+reference run unchanged. The compute is hand-written sm_100a CUDA reached through the C ABI (srvp_b200/_lib.py);
+there is no PyTorch/CPU fallback for the conv-VAE path.
+
+Random draws follow the reference's consumption order: skip-frame `randint`, per-video `randperm`,
+y_0 noise, then one z noise per observed frame. `noise_device` selects which torch generator the Gaussian noise comes
+from: 'cpu' (default; bit-identical stream to the reference run on CPU, used for parity) or 'cuda'.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import conv, utils
+from .mlp import MLP
+from .. import engine
+
+
+class StochasticLatentResidualVideoPredictor(nn.Module):
+    def __init__(self, nx, nc, nf, nhx, ny, nz, skipco, nt_inf, nh_inf, nlayers_inf, nh_res, nlayers_res, archi):
+        super().__init__()
+        self.nx, self.nc, self.ny, self.nz = nx, nc, ny, nz
+        self.skipco = skipco
+        self.nt_inf, self.nh_inf, self.nlayers_inf = nt_inf, nh_inf, nlayers_inf
+        self.nh_res, self.nlayers_res = nh_res, nlayers_res
+        self.nhx = nhx
+        self.noise_device = 'cpu'
+        # construction order = reference order (module/srvp.py:124-137): it fixes the same-seed default initialisation
+        self.encoder = conv.encoder_factory(archi, nx, nc, nhx, nf)
+        self.decoder = conv.decoder_factory(archi, nx, nc, nh_inf + ny, nf, skipco)
+        self.w_proj = nn.Sequential(nn.Linear(nhx, nh_inf), nn.ReLU(inplace=True))
+        self.w_inf = nn.Sequential(nn.Linear(nh_inf, nh_inf), nn.Tanh())
+        self.q_y = MLP(nhx * nt_inf, nh_inf, ny * 2, nlayers_inf)
+        self.inf_z = nn.LSTM(nhx, nh_inf, 1)
+        self.q_z = nn.Linear(nh_inf, nz * 2)
+        self.p_z = MLP(ny, nh_res, nz * 2, nlayers_res)
+        self.dynamics = MLP(ny + nz, nh_res, ny, nlayers_res)
+
+    def init(self, res_gain=1.41):
+        """module/srvp.py:139-154"""
+        for net in (self.encoder, self.decoder):
+            net.apply(lambda m: utils.init_weight(m, init_type='normal', init_gain=0.02))
+        self.dynamics.apply(lambda m: utils.init_weight(m, init_type='orthogonal', init_gain=res_gain))
+
+    # ------------------------------------------------------------------------------------------------ noise
+    def _normal(self, shape, like):
+        if self.noise_device == 'cpu':
+            return torch.empty(shape, dtype=torch.float32).normal_().to(like.device, non_blocking=True)
+        return torch.empty(shape, dtype=torch.float32, device=like.device).normal_()
+
+    def _rsample(self, raw_params):
+        loc, raw_scale = torch.chunk(raw_params, 2, -1)
+        scale = nn.functional.softplus(raw_scale) + 1e-8
+        return loc + self._normal(loc.shape, loc) * scale
+
+    # ------------------------------------------------------------------------------------------------ encode / decode
+    def _encode_fused(self, x):
+        """Returns hx (T, B, nhx) and a SkipHandle (or None). Skip frames: random per video in training, last otherwise."""
+        nt, bsz = x.shape[0], x.shape[1]
+        handle = engine.SkipHandle() if self.skipco else None
+        hx = engine.encoder_apply(self.encoder, x.reshape(nt * bsz, *x.shape[2:]), handle).view(nt, bsz, self.nhx)
+        if self.skipco:
+            if self.training:
+                t = torch.randint(nt, size=(bsz,))
+            else:
+                t = torch.full((bsz,), nt - 1, dtype=torch.long)
+            sel = (t * bsz + torch.arange(bsz)).to(torch.int32)          # encoder frame feeding each video's skip
+            inv = torch.full((nt * bsz,), -1, dtype=torch.int32)
+            inv[sel.long()] = torch.arange(bsz, dtype=torch.int32)
+            handle.T, handle.B = nt, bsz
+            handle.frame_map = sel.to(x.device, non_blocking=True)        # (B,), expanded per decode call
+            handle.inv_map = inv.to(x.device, non_blocking=True)
+        return hx, handle
+
+    def encode(self, x):
+        """module/srvp.py:156-193. Skips are returned as (B, C, H, W) fp32 tensors, deepest first."""
+        hx, handle = self._encode_fused(x)
+        if handle is None:
+            return hx, None
+        from .. import ops
+        skips = []
+        for (z, st, C, res) in handle.levels:
+            src = ops.Src(z, C, st.scale, st.shift, handle.frame_map, 0, 0, True)
+            skips.append(ops.nhwc_to_nchw_f32(ops.materialize(src, x.shape[1], res, res), C))
+        return hx, skips
+
+    def _decode_fused(self, w, y, levels, sel, handle):
+        nt, bsz = y.shape[0], y.shape[1]
+        dec_inp = torch.cat([w.repeat(nt, 1, 1).view(nt * bsz, self.nh_inf), y.reshape(nt * bsz, self.ny)], 1)
+        frame_map = None
+        if levels is not None:
+            frame_map = sel.repeat(nt)                                    # decoder frame (t, b) -> source frame of video b
+        x_flat = engine.decoder_apply(self.decoder, dec_inp, levels, frame_map, handle)
+        return x_flat.view(nt, bsz, *x_flat.shape[1:])
+
+    def decode(self, w, y, skip):
+        """module/srvp.py:195-227. skip: list of (B, C, H, W) tensors (deepest first) or None."""
+        assert skip is None and not self.skipco or self.skipco and skip is not None
+        levels, sel = None, None
+        if skip is not None:
+            from .. import ops
+            levels = [ops.nchw_to_nhwc_bf16(s.contiguous().float(), s.shape[1]) for s in skip]
+            sel = torch.arange(y.shape[1], dtype=torch.int32, device=y.device)
+        return self._decode_fused(w, y, levels, sel, None)
+
+    # ------------------------------------------------------------------------------------------------ inference nets
+    def infer_w(self, hx):
+        """module/srvp.py:229-256"""
+        nt, bsz = hx.shape[0], hx.shape[1]
+        if self.training:
+            t = torch.stack([torch.randperm(nt)[:self.nt_inf] for _ in range(bsz)], 1).to(hx.device)
+            index = torch.arange(bsz, device=hx.device).repeat(self.nt_inf, 1)
+            h = hx[t.view(-1), index.view(-1)].view(self.nt_inf, bsz, self.nhx)
+        else:
+            h = hx[-self.nt_inf:]
+        return self.w_inf(self.w_proj(h).sum(0))
+
+    def infer_y(self, hx):
+        """module/srvp.py:258-278"""
+        q_y_0_params = self.q_y(hx.permute(1, 0, 2).reshape(hx.shape[1], self.nt_inf * self.nhx))
+        return self._rsample(q_y_0_params), q_y_0_params
+
+    def infer_z(self, hx):
+        """module/srvp.py:280-298"""
+        q_z_params = self.q_z(hx)
+        return self._rsample(q_z_params), q_z_params
+
+    def _residual_step(self, y_t, z_tp1, dt):
+        """module/srvp.py:300-323"""
+        res_tp1 = dt * self.dynamics(torch.cat([y_t, z_tp1], 1))
+        return y_t + res_tp1, res_tp1
+
+    def generate(self, y_0, hx, nt, dt, remove_intermediate=True):
+        """module/srvp.py:325-413"""
+        y, z, q_z_params, p_z_params, res = [y_0], [], [], [], []
+        hx_z = self.inf_z(hx)[0] if len(hx) > 0 else []
+        assert (1 / dt).is_integer()
+        oversampling = int(1 / dt)
+        y_tm1, t_data = y_0, 0
+        for t in np.linspace(dt, nt - 1, oversampling * (nt - 1)):
+            prev_t_data, t_data = t_data, int(math.ceil(t))
+            if t_data != prev_t_data:
+                p_z_t_params = self.p_z(y_tm1)
+                p_z_params.append(p_z_t_params)
+                if t_data < len(hx):
+                    z_t, q_z_t_params = self.infer_z(hx_z[t_data])
+                    q_z_params.append(q_z_t_params)
+                else:
+                    assert not self.training
+                    z_t = self._rsample(p_z_t_params)
+                z.append(z_t)
+            else:
+                z_t = z[-1]
+            y_t, res_t = self._residual_step(y_tm1, z_t, dt)
+            y_tm1 = y_t
+            if not remove_intermediate or t.is_integer():
+                y.append(y_t)
+            res.append(res_t)
+        y = torch.stack(y)
+        z = torch.stack(z) if len(z) > 0 else None
+        q_z_params = torch.stack(q_z_params) if len(q_z_params) > 0 else None
+        p_z_params = torch.stack(p_z_params) if len(p_z_params) > 0 else None
+        return y, z, q_z_params, p_z_params, torch.stack(res)
+
+    def forward(self, x, nt, dt, remove_intermediate=True):
+        """module/srvp.py:415-470: returns (x_, y, z, w, q_y_0_params, q_z_params, p_z_params, res)."""
+        hx, handle = self._encode_fused(x)
+        w = self.infer_w(hx)
+        y_0, q_y_0_params = self.infer_y(hx[:self.nt_inf])
+        y, z, q_z_params, p_z_params, res = self.generate(y_0, hx, nt, dt, remove_intermediate=remove_intermediate)
+        levels = handle.levels if handle is not None else None
+        sel = handle.frame_map if handle is not None else None
+        x_ = self._decode_fused(w, y, levels, sel, handle)
+        return x_, y, z, w, q_y_0_params, q_z_params, p_z_params, res

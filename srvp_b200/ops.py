@@ -143,3 +143,157 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
             a.stats_partial = ptr(stats_partial)
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
     return out, stats_partial
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_to_nhwc_bf16(x, cpad):
+    """(frames, C, H, W) fp32 -> (frames, H, W, cpad) bf16, zero padded channels."""
+    F_, C, H, W = x.shape
+    out = torch.empty(F_, H, W, cpad, dtype=torch.bfloat16, device=x.device)
+    check(lib().srvp_nchw_f32_to_nhwc_bf16(ptr(x), ptr(out), c_int(F_), c_int(C), c_int(H), c_int(W), c_int(cpad), stream_ptr()),
+          'nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw_f32(t, C):
+    F_, H, W, cp = t.shape
+    out = torch.empty(F_, C, H, W, dtype=torch.float32, device=t.device)
+    check(lib().srvp_nhwc_bf16_to_nchw_f32(ptr(t), ptr(out), c_int(F_), c_int(C), c_int(H), c_int(W), c_int(cp), stream_ptr()),
+          'nhwc_to_nchw')
+    return out
+
+
+def materialize(src, frames, H, W):
+    cs = _lib.ConvSrc()
+    _fill_src(cs, src)
+    out = torch.empty(frames, H, W, src.channels, dtype=torch.bfloat16, device=src.tensor.device)
+    check(lib().srvp_materialize_src(ctypes.byref(cs), ptr(out), c_int(frames), c_int(H), c_int(W), stream_ptr()), 'materialize_src')
+    return out
+
+
+def transpose_last2(t):
+    """(A, B, C) fp32 -> (A, C, B)."""
+    A, B, C = t.shape
+    out = torch.empty(A, C, B, dtype=torch.float32, device=t.device)
+    check(lib().srvp_transpose_last2_f32(ptr(t), ptr(out), c_int(A), c_int(B), c_int(C), stream_ptr()), 'transpose_last2')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+class BNState:
+    """Per-layer forward affine and saved statistics (all fp32, (C,))."""
+    __slots__ = ('scale', 'shift', 'mean', 'invstd')
+
+    def __init__(self, C, device):
+        buf = torch.empty(4, C, dtype=torch.float32, device=device)
+        self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
+
+
+def bn_finalize(partial, count, bn, state, training_update=True, eps=1e-5, momentum=0.1):
+    """partial: (rows, C, 2). bn: torch.nn.BatchNorm2d parameter container (weight, bias, running_*)."""
+    rows, C = partial.shape[0], partial.shape[1]
+    rm = bn.running_mean if training_update else None
+    rv = bn.running_var if training_update else None
+    check(lib().srvp_bn_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(bn.weight), ptr(bn.bias),
+                                ctypes.c_float(eps), ctypes.c_float(momentum), ptr(rm), ptr(rv), ptr(state.scale), ptr(state.shift),
+                                ptr(state.mean), ptr(state.invstd), stream_ptr()), 'bn_finalize')
+    return state
+
+
+def bn_eval_params(bn, state, eps=1e-5):
+    C = bn.weight.shape[0]
+    check(lib().srvp_bn_eval_params(ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ctypes.c_float(eps),
+                                   ptr(state.scale), ptr(state.shift), c_int(C), stream_ptr()), 'bn_eval_params')
+    return state
+
+
+def channel_stats(z2d):
+    """z2d: (rows, C) bf16 -> partial (nblocks, C, 2)."""
+    rows, C = z2d.shape
+    nb = lib().srvp_channel_stats_rows(c_i64(rows))
+    partial = torch.empty(nb, C, 2, dtype=torch.float32, device=z2d.device)
+    check(lib().srvp_channel_stats(ptr(z2d), c_i64(rows), c_int(C), ptr(partial), stream_ptr()), 'channel_stats')
+    return partial
+
+
+def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_coff=0, skip=None, skip_coff=0, nt=0, B=0,
+           inv_map=None, lrelu=True):
+    """Full BN(train)+LeakyReLU(+pool/upsample) backward. Returns dz (bf16, (frames,H,W,C)); accumulates dgamma/dbeta."""
+    dev = z.device
+    g = torch.empty(frames, H, W, C, dtype=torch.bfloat16, device=dev)
+    rows = lib().srvp_bn_bwd_reduce_rows(c_int(frames), c_int(H), c_int(W), c_int(da_mode))
+    partial = torch.empty(rows, C, 2, dtype=torch.float32, device=dev)
+    a = _lib.BnBwdArgs()
+    a.z, a.scale, a.shift, a.mean, a.invstd = ptr(z), ptr(state.scale), ptr(state.shift), ptr(state.mean), ptr(state.invstd)
+    a.da, a.da_cpitch, a.da_coff, a.da_mode = ptr(da), da.shape[-1], da_coff, da_mode
+    if skip is not None:
+        a.skip, a.skip_cpitch, a.skip_coff, a.nt, a.B, a.inv_map = ptr(skip), skip.shape[-1], skip_coff, nt, B, ptr(inv_map)
+    a.g, a.partial = ptr(g), ptr(partial)
+    a.frames, a.H, a.W, a.C, a.lrelu = frames, H, W, C, int(lrelu)
+    check(lib().srvp_bn_bwd_reduce(ctypes.byref(a), stream_ptr()), 'bn_bwd_reduce')
+    c12 = torch.empty(2, C, dtype=torch.float32, device=dev)
+    count = float(frames * H * W)
+    check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(c12[0]), ptr(c12[1]),
+                                    ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
+    check(lib().srvp_bn_bwd_apply(ptr(g), ptr(z), ptr(gamma), ptr(state.mean), ptr(state.invstd), ptr(c12[0]), ptr(c12[1]),
+                                 c_i64(frames * H * W), c_int(C), stream_ptr()), 'bn_bwd_apply')
+    return g
+
+
+def sigmoid_bwd(dxhat, xhat):
+    """(frames, C, H, W) fp32 x2 -> dz (frames, H, W, 16) bf16."""
+    F_, C, H, W = xhat.shape
+    out = torch.empty(F_, H, W, 16, dtype=torch.bfloat16, device=xhat.device)
+    check(lib().srvp_sigmoid_bwd_nchw_to_nhwc16(ptr(dxhat), ptr(xhat), ptr(out), c_int(F_), c_int(C), c_int(H), c_int(W), stream_ptr()),
+          'sigmoid_bwd')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError(t.dtype)
+
+
+def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=False, split_k=0):
+    """c[m, n] (+)= act(sum_k a[m, k] * b[n, k] + bias). a, b, c are 2-D (possibly transposed) views of CUDA tensors."""
+    M, K = a.shape
+    N, K2 = b.shape
+    assert K == K2 and tuple(c.shape) == (M, N), (a.shape, b.shape, c.shape)
+    g = _lib.GemmArgs()
+    g.a, g.a_dtype, g.a_sm, g.a_sk = ctypes.c_void_p(a.data_ptr()), _dt(a), a.stride(0), a.stride(1)
+    g.b, g.b_dtype, g.b_sn, g.b_sk = ctypes.c_void_p(b.data_ptr()), _dt(b), b.stride(0), b.stride(1)
+    g.c, g.c_dtype, g.c_sm, g.c_sn = ctypes.c_void_p(c.data_ptr()), _dt(c), c.stride(0), c.stride(1)
+    if K == 1 or M == 1:
+        g.a_sk = 1 if a.stride(1) == 1 or K == 1 else g.a_sk
+    g.bias = ptr(bias)
+    g.bias_on_m = int(bias_on_m)
+    g.M, g.N, g.K = M, N, K
+    g.act, g.accumulate, g.split_k = act, int(accumulate), split_k
+    check(lib().srvp_gemm(ctypes.byref(g), stream_ptr()), 'gemm')
+    return c
+
+
+def bn_tanh_rows_fwd(z, bn, state, training, update_running=True, eps=1e-5, momentum=0.1):
+    """z: (rows, C) fp32 -> tanh(bn(z)) fp32. Training: batch statistics; eval: running statistics."""
+    rows, C = z.shape
+    out = torch.empty_like(z)
+    if not training:
+        bn_eval_params(bn, state, eps)
+    rm = bn.running_mean if (training and update_running) else None
+    rv = bn.running_var if (training and update_running) else None
+    check(lib().srvp_bn_tanh_rows_fwd(ptr(z), c_int(rows), c_int(C), ptr(bn.weight), ptr(bn.bias), ctypes.c_float(eps),
+                                     ctypes.c_float(momentum), ptr(rm), ptr(rv), c_int(int(training)), ptr(state.scale), ptr(state.shift),
+                                     ptr(state.mean), ptr(state.invstd), ptr(out), stream_ptr()), 'bn_tanh_rows_fwd')
+    return out
+
+
+def bn_tanh_rows_bwd(dout, out, z, gamma, state, dgamma, dbeta):
+    rows, C = z.shape
+    dz = torch.empty_like(z)
+    check(lib().srvp_bn_tanh_rows_bwd(ptr(dout), ptr(out), ptr(z), c_int(rows), c_int(C), ptr(gamma), ptr(state.mean), ptr(state.invstd),
+                                     ptr(dz), ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_tanh_rows_bwd')
+    return dz
