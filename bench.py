@@ -1,0 +1,254 @@
+"""Benchmark of the SRVP hot path: frames/s of one full training step (forward + ELBO + backward + Adam).
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+  workload  BAIR config of BASELINE.json: VGG64 skipco nc=3 64x64, seq_len 12, batch 192 per GPU (weak scaling),
+            ny=nz=50, nt_inf=2, 2 Euler steps, obs_scale 0.71 (reference README.md:127); synthetic uniform frames.
+  value     frames/s with the batch already resident in HBM (device timed, CUDA events, max over ranks)
+  e2e       same step through the public API from pinned HOST frames: H2D of the batch and D2H of the loss inside the
+            timed region
+  roofline  dominant kernel family: algorithmic dense FLOPs / CUDA-event time vs the measured bf16 peak
+  cpu_baseline / --impl reference: the reference algorithm (oracle port, torch CPU fp32) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(nx=64, nc=3, nf=64, nhx=128, ny=50, nz=50, skipco=True, nt_inf=2, nh_inf=256, nlayers_inf=3, nh_res=512, nlayers_res=4,
+           archi='vgg')
+ARG_ORDER = ['nx', 'nc', 'nf', 'nhx', 'ny', 'nz', 'skipco', 'nt_inf', 'nh_inf', 'nlayers_inf', 'nh_res', 'nlayers_res', 'archi']
+LOSS = dict(obs_scale=0.71, beta_y=1.0, beta_z=1.0, l2_res=1.0)
+SEQ_LEN, BATCH, DT = 12, 192, 0.5
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf=d['bf16_tflops_sustained'], tf_burst=d['bf16_tflops'], hbm=d['hbm_gbs'], src='measured')
+    return dict(tf=1400.0, tf_burst=1590.0, hbm=6650.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.max_mhz, self.reasons = None, set()
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [v.strip() for v in out.split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+def elbo_loss(out, x):
+    import torch.distributions as distrib
+    from srvp_b200.module import utils
+    x_, y, z, _, q_y_0_params, q_z_params, p_z_params, res = out
+    n = x.shape[1]
+    nll = utils.neg_logprob(x_, x, scale=LOSS['obs_scale']).sum()
+    kl_y_0 = distrib.kl_divergence(utils.make_normal_from_raw_params(q_y_0_params), distrib.Normal(0, 1)).sum()
+    kl_z = distrib.kl_divergence(utils.make_normal_from_raw_params(q_z_params), utils.make_normal_from_raw_params(p_z_params)).sum()
+    loss = nll + LOSS['beta_y'] * kl_y_0 + LOSS['beta_z'] * kl_z + LOSS['l2_res'] * torch.norm(res, p=2, dim=2).sum()
+    return loss / n
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from srvp_b200 import ops, _lib
+    from srvp_b200.module.srvp import StochasticLatentResidualVideoPredictor
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(1)
+    model = StochasticLatentResidualVideoPredictor(*[CFG[k] for k in ARG_ORDER])
+    model.init(res_gain=1.41)
+    model = model.to(dev).train()
+    model.noise_device = 'cuda'
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=3e-4, fused=True)
+    gen = torch.Generator().manual_seed(123 + rank)
+    # several distinct host batches (pinned) so that the e2e loop really moves data; each batch is 113 MB fp32
+    host = [torch.rand(SEQ_LEN, BATCH, CFG['nc'], 64, 64, generator=gen).pin_memory() for _ in range(2)]
+    xdev = host[0].to(dev)
+
+    def sync_grads():
+        if world > 1:
+            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+                p.grad.copy_(g)
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        out = model(x, SEQ_LEN, dt=DT)
+        loss = elbo_loss(out, x)
+        loss.backward()
+        sync_grads()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(xdev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.lib().srvp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(xdev)
+    e1.record()
+    barrier()
+    launches = _lib.lib().srvp_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    # end-to-end: host frames -> device, step, loss -> host, every step
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        xb = host[i % len(host)].to(dev, non_blocking=True)
+        lv = step(xb).item()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # per-kernel profile (2 extra steps with CUDA events around every launch)
+    ops.PROFILE = {}
+    for _ in range(2):
+        step(xdev)
+    torch.cuda.synchronize()
+    prof = ops.summarize_profile(ops.PROFILE)
+    ops.PROFILE = None
+    pk = peaks()
+    tot_ms = sum(v['ms'] for v in prof.values())
+    dom = max((k for k in prof if prof[k]['flops'] > 0), key=lambda k: prof[k]['ms'])
+    d = prof[dom]
+    achieved = d['flops'] / (d['ms'] * 1e-3) / 1e12
+    roofline = dict(bound='tensor', kernel=dom, achieved=round(achieved, 1), peak=pk['tf'], unit='TFLOP/s', frac=round(achieved / pk['tf'], 4),
+                    traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)', share_of_kernel_time=round(d['ms'] / tot_ms, 3),
+                    launches_per_step=d['launches'] // 2, avg_launch_ms=round(d['ms'] / d['launches'], 4))
+    breakdown = {k: dict(ms_per_step=round(v['ms'] / 2, 3), launches=v['launches'] // 2,
+                         tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['flops'] else None,
+                         gbs=round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1) if v['bytes'] else None) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
+    if rank != 0:
+        return
+    frames = SEQ_LEN * BATCH * world
+    line = dict(metric='frames/sec training step (BAIR 64x64 seq12 bs192)', value=round(frames * args.steps / (ms * 1e-3), 1), unit='frames/s',
+                n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
+                config=dict(workload='BAIR VGG64 skipco nc=3 64x64 seq_len=12 batch=192/GPU ny=nz=50 nt_inf=2 n_euler_steps=2; fwd+ELBO+bwd+Adam',
+                            global_batch=BATCH * world, seq_len=SEQ_LEN, parallelism=f'dp{world}',
+                            l2='inputs larger than L2: 113 MB batch, >10 GB of activations per step'),
+                e2e=dict(value=round(frames * args.steps / (ms_e2e * 1e-3), 1), unit='frames/s', h2d_bytes_per_step=host[0].numel() * 4,
+                         d2h_bytes_per_step=4),
+                gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline, kernel_breakdown=breakdown, loss=lv)
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(steps=1, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(steps, warmup, batch=8):
+    """The reference algorithm (oracle port of module/srvp.py + train.py:88-119, torch CPU fp32) on the host cores."""
+    from oracle import srvp_oracle as O
+    from srvp_b200.module.srvp import StochasticLatentResidualVideoPredictor
+    torch.manual_seed(1)
+    m = StochasticLatentResidualVideoPredictor(*[CFG[k] for k in ARG_ORDER])
+    m.init(res_gain=1.41)
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in m.state_dict().items()}
+    ps = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.Adam(ps, lr=3e-4)
+    x = torch.rand(SEQ_LEN, batch, CFG['nc'], 64, 64, generator=torch.Generator().manual_seed(123))
+
+    def step():
+        opt.zero_grad()
+        rnd = O.draw_randoms(CFG, SEQ_LEN, SEQ_LEN, batch, training=True)
+        o = O.forward(sd, CFG, x, SEQ_LEN, DT, rnd, training=True)
+        loss = O.elbo(o, x, LOSS)[0]
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=round(SEQ_LEN * batch / dt, 2), unit='frames/s', cores=torch.get_num_threads(), host_cpus=os.cpu_count(), kind='port',
+                sample=f'{steps} training step(s) of the same workload at batch {batch} (of {BATCH}), torch {torch.__version__} CPU fp32, '
+                       f'{dt:.2f} s/step; frames/s is batch-size independent on CPU')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 3)), 1
+    cb = cpu_baseline(steps=steps, warmup=warm)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    line = dict(metric='frames/sec training step (BAIR 64x64 seq12 bs192)', value=cb['value'], unit='frames/s', impl='reference',
+                n_gpus=world, steps=steps, warmup=warm, ms_per_step=round(SEQ_LEN * 8 / cb['value'] * 1e3, 1), higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='BAIR VGG64 skipco nc=3 64x64 seq_len=12 batch=192/GPU ny=nz=50 nt_inf=2 n_euler_steps=2; fwd+ELBO+bwd+Adam',
+                            global_batch=BATCH * world, seq_len=SEQ_LEN, parallelism='cpu'),
+                cpu_baseline=cb, e2e=dict(value=cb['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

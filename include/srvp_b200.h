@@ -25,6 +25,8 @@ typedef uint16_t srvp_bf16; /* raw bfloat16 bits */
 
 const char* srvp_last_error(void);
 int srvp_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long srvp_launch_count(void);
 /* Number of SMs of the current device (grid sizing for persistent kernels). */
 int srvp_num_sms(void);
 

@@ -65,6 +65,7 @@ def lib():
                                f'or `make -C srvp_b200/csrc`. srvp_b200 has no CPU / PyTorch fallback.')
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.srvp_last_error.restype = ctypes.c_char_p
+        _lib.srvp_launch_count.restype = ctypes.c_uint64
         for name in EXPORTS:
             getattr(_lib, name)  # AttributeError if the header and the library disagree
     return _lib
@@ -72,7 +73,7 @@ def lib():
 
 # every symbol declared in include/srvp_b200.h
 EXPORTS = [
-    'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
+    'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_launch_count', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
     'srvp_pack_conv3x3_weights', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16', 'srvp_nhwc_bf16_to_nchw_f32',
     'srvp_materialize_src', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',

@@ -18,7 +18,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -43,4 +46,5 @@ int num_sms_cached() {
 
 extern "C" const char* srvp_last_error(void) { return srvp::g_err; }
 extern "C" int srvp_version(void) { return 100; }
+extern "C" unsigned long long srvp_launch_count(void) { return srvp::g_launches; }
 extern "C" int srvp_num_sms(void) { return srvp::num_sms_cached(); }

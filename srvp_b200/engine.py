@@ -108,7 +108,7 @@ def _encoder_fwd(enc, x, training, want_stats_update=True):
         src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, blk.in_mode, prev.lrelu)
         wp = ops.pack_conv3x3(blk.conv.weight, 'conv')
         st = BNState(blk.cout, dev)
-        z, partial = ops.conv3x3([src], wp, F_, blk.res, blk.res, blk.cout, stats=training)
+        z, partial = ops.conv3x3([src], wp, F_, blk.res, blk.res, blk.cout, stats=training, cin_real=blk.cin)
         if training:
             ops.bn_finalize(partial, float(F_ * blk.res * blk.res), blk.bn, st, training_update=want_stats_update)
         else:
@@ -270,7 +270,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     dz = ops.sigmoid_bwd(d_xhat.contiguous(), c.x_hat)  # (F,64,64,16)
     ops.wgrad3x3([c.final_src], dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT')
     wp = ops.pack_conv3x3(final.weight, 'convT_dgrad')
-    da, _ = ops.conv3x3([Src(dz, 16)], wp, F_, 64, 64, final.in_channels)
+    da, _ = ops.conv3x3([Src(dz, 16)], wp, F_, 64, 64, final.in_channels, cin_real=nc)
     da_mode, da_coff = SRC_DIRECT, 0
     skip_grads = {}
     for li in range(len(plan) - 1, -1, -1):

@@ -9,6 +9,49 @@ from . import _lib
 from ._lib import c_int, c_i64, check, lib, ptr, stream_ptr
 
 
+# ------------------------------------------------------------------------------------------------ per-kernel timing
+# bench.py sets PROFILE = {} for a few extra steps: every wrapper below then brackets its launches with CUDA events on the
+# current stream and records (events, algorithmic flops, algorithmic bytes); summarize_profile() reduces them after a sync.
+PROFILE = None
+
+
+def profiled(name):
+    def deco(fn):
+        def wrapper(*args, **kwargs):
+            if PROFILE is None:
+                return fn(*args, **kwargs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _WORK.append([0.0, 0.0])
+            out = fn(*args, **kwargs)
+            e1.record()
+            fl, by = _WORK.pop()
+            PROFILE.setdefault(name, []).append((e0, e1, fl, by))
+            return out
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
+_WORK = []
+
+
+def _account(flops=0.0, nbytes=0.0):
+    if _WORK:
+        _WORK[-1][0] += flops
+        _WORK[-1][1] += nbytes
+
+
+def summarize_profile(profile):
+    """{name: dict(launches, ms, flops, bytes)} -- call after torch.cuda.synchronize()."""
+    out = {}
+    for name, recs in profile.items():
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs)
+        out[name] = dict(launches=len(recs), ms=ms, flops=sum(r[2] for r in recs), bytes=sum(r[3] for r in recs))
+    return out
+
+
 @dataclass
 class Src:
     """One input of a fused 3x3 convolution: a raw NHWC bf16 tensor + the fused BN/activation/resampling."""
@@ -51,6 +94,7 @@ def padded_k(k):
     return 16 if k <= 16 else pad_to(k, 64)
 
 
+@profiled('pack_conv3x3')
 def pack_conv3x3(weight, kind, out=None):
     """fp32 (.,.,3,3) weight -> packed bf16 B operand."""
     assert weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
@@ -80,6 +124,7 @@ def _fill_src(cs, s):
     cs.lrelu = int(s.lrelu)
 
 
+@profiled('wgrad3x3')
 def wgrad3x3(srcs, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'."""
     a = _lib.Wgrad3x3Args()
@@ -97,10 +142,12 @@ def wgrad3x3(srcs, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0
     else:
         a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
     check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
+    _account(2.0 * frames * H * W * cout * cin * 9, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel())
     return dw
 
 
-def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False):
+@profiled('conv3x3')
+def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None):
     """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None)."""
     a = _lib.Conv3x3Args()
     a.nsrc = len(srcs)
@@ -142,10 +189,14 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
             stats_partial = torch.empty(nmt, cout, 2, dtype=torch.float32, device=dev)
             a.stats_partial = ptr(stats_partial)
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
+    cin_real = cin_real if cin_real is not None else sum(s.channels for s in srcs)
+    obytes = out.numel() * out.element_size()
+    _account(2.0 * frames * H * W * cout * cin_real * 9, sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
     return out, stats_partial
 
 
 # ------------------------------------------------------------------------------------------------ layout
+@profiled('nchw_to_nhwc_bf16')
 def nchw_to_nhwc_bf16(x, cpad):
     """(frames, C, H, W) fp32 -> (frames, H, W, cpad) bf16, zero padded channels."""
     F_, C, H, W = x.shape
@@ -155,6 +206,7 @@ def nchw_to_nhwc_bf16(x, cpad):
     return out
 
 
+@profiled('nhwc_to_nchw_f32')
 def nhwc_to_nchw_f32(t, C):
     F_, H, W, cp = t.shape
     out = torch.empty(F_, C, H, W, dtype=torch.float32, device=t.device)
@@ -163,6 +215,7 @@ def nhwc_to_nchw_f32(t, C):
     return out
 
 
+@profiled('materialize')
 def materialize(src, frames, H, W):
     cs = _lib.ConvSrc()
     _fill_src(cs, src)
@@ -171,6 +224,7 @@ def materialize(src, frames, H, W):
     return out
 
 
+@profiled('transpose_last2')
 def transpose_last2(t):
     """(A, B, C) fp32 -> (A, C, B)."""
     A, B, C = t.shape
@@ -189,6 +243,7 @@ class BNState:
         self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
 
 
+@profiled('bn_finalize')
 def bn_finalize(partial, count, bn, state, training_update=True, eps=1e-5, momentum=0.1):
     """partial: (rows, C, 2). bn: torch.nn.BatchNorm2d parameter container (weight, bias, running_*)."""
     rows, C = partial.shape[0], partial.shape[1]
@@ -200,6 +255,7 @@ def bn_finalize(partial, count, bn, state, training_update=True, eps=1e-5, momen
     return state
 
 
+@profiled('bn_eval_params')
 def bn_eval_params(bn, state, eps=1e-5):
     C = bn.weight.shape[0]
     check(lib().srvp_bn_eval_params(ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ctypes.c_float(eps),
@@ -207,6 +263,7 @@ def bn_eval_params(bn, state, eps=1e-5):
     return state
 
 
+@profiled('channel_stats')
 def channel_stats(z2d):
     """z2d: (rows, C) bf16 -> partial (nblocks, C, 2)."""
     rows, C = z2d.shape
@@ -216,6 +273,7 @@ def channel_stats(z2d):
     return partial
 
 
+@profiled('bn_bwd')
 def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_coff=0, skip=None, skip_coff=0, nt=0, B=0,
            inv_map=None, lrelu=True):
     """Full BN(train)+LeakyReLU(+pool/upsample) backward. Returns dz (bf16, (frames,H,W,C)); accumulates dgamma/dbeta."""
@@ -237,9 +295,12 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
                                     ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
     check(lib().srvp_bn_bwd_apply(ptr(g), ptr(z), ptr(gamma), ptr(state.mean), ptr(state.invstd), ptr(c12[0]), ptr(c12[1]),
                                  c_i64(frames * H * W), c_int(C), stream_ptr()), 'bn_bwd_apply')
+    n = float(frames * H * W * C)
+    _account(0.0, 2.0 * n * (2 + 3) + 2.0 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0))
     return g
 
 
+@profiled('sigmoid_bwd')
 def sigmoid_bwd(dxhat, xhat):
     """(frames, C, H, W) fp32 x2 -> dz (frames, H, W, 16) bf16."""
     F_, C, H, W = xhat.shape
@@ -258,6 +319,7 @@ def _dt(t):
     raise TypeError(t.dtype)
 
 
+@profiled('gemm')
 def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=False, split_k=0):
     """c[m, n] (+)= act(sum_k a[m, k] * b[n, k] + bias). a, b, c are 2-D (possibly transposed) views of CUDA tensors."""
     M, K = a.shape
@@ -274,9 +336,11 @@ def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=F
     g.M, g.N, g.K = M, N, K
     g.act, g.accumulate, g.split_k = act, int(accumulate), split_k
     check(lib().srvp_gemm(ctypes.byref(g), stream_ptr()), 'gemm')
+    _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N)
     return c
 
 
+@profiled('bn_tanh_rows_fwd')
 def bn_tanh_rows_fwd(z, bn, state, training, update_running=True, eps=1e-5, momentum=0.1):
     """z: (rows, C) fp32 -> tanh(bn(z)) fp32. Training: batch statistics; eval: running statistics."""
     rows, C = z.shape
@@ -291,6 +355,7 @@ def bn_tanh_rows_fwd(z, bn, state, training, update_running=True, eps=1e-5, mome
     return out
 
 
+@profiled('bn_tanh_rows_bwd')
 def bn_tanh_rows_bwd(dout, out, z, gamma, state, dgamma, dbeta):
     rows, C = z.shape
     dz = torch.empty_like(z)
