@@ -66,6 +66,9 @@ typedef struct {
   int32_t out_cpitch, out_coff;
   float* stats_partial;   /* optional [num_mtiles][cout][2] per-tile (sum, sum of squares) of the stored bf16 values */
   float* out_f32_nchw;    /* EPI_SIGMOID_NCHW_F32: (frames, cout, H, W) fp32 */
+  srvp_bf16* a_out;       /* optional: the loader also stores the conv input it computed (BN+LReLU+pool/upsample/concat applied),
+                             NHWC (frames,H,W,a_out_cpitch); the weight-gradient kernel reads it back */
+  int32_t a_out_cpitch;
 } srvp_conv3x3_args;
 
 /* Number of M tiles (rows of stats_partial) srvp_conv3x3 will use for this geometry / channel count. */
@@ -82,17 +85,18 @@ int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32_t n_real, 
 
 /* Weight gradient of the same convolutions (autograd of module/conv.py:198-220, :333-354 via train.py:119):
  * dw[co*stride_cout + ci*stride_cin + (flip ? 8-tap : tap)] += sum_p dz[p, co] * a[p + tap offset, ci], where `a` is
- * recomputed by the loader from the fused activation sources (same semantics as srvp_conv3x3's sources).
+ * the conv input saved by the forward pass (a_out).
  * nn.Conv2d weight (Cout,Cin,3,3): stride_cout = Cin*9, stride_cin = 9, flip = 0;
  * nn.ConvTranspose2d weight (Cin,Cout,3,3): stride_cout = 9, stride_cin = Cout*9, flip = 1. dw is ACCUMULATED into. */
 typedef struct {
-  srvp_conv_src act[2];
-  int32_t nact;
-  const srvp_bf16* dz;  /* NHWC bf16 gradient w.r.t. the raw conv output */
-  int32_t dz_channels;  /* channels to read (padded count, multiple of 8) */
+  const srvp_bf16* act;  /* materialised conv input a, NHWC bf16 (srvp_conv3x3_args.a_out of the forward call) */
+  int32_t act_channels;  /* channels to read (padded count, multiple of 8) */
+  int32_t act_cpitch, act_coff;
+  const srvp_bf16* dz;   /* NHWC bf16 gradient w.r.t. the raw conv output */
+  int32_t dz_channels;   /* channels to read (padded count, multiple of 8) */
   int32_t dz_cpitch, dz_coff;
   int32_t frames, H, W;
-  int32_t cout, cin;    /* real channel counts (padded channels are not written) */
+  int32_t cout, cin;     /* real channel counts (padded channels are not written) */
   float* dw;
   int64_t stride_cout, stride_cin;
   int32_t flip;

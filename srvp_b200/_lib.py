@@ -25,12 +25,12 @@ class ConvSrc(ctypes.Structure):
 class Conv3x3Args(ctypes.Structure):
     _fields_ = [('src', ConvSrc * 2), ('nsrc', c_int), ('wpack', c_ptr), ('frames', c_int), ('H', c_int), ('W', c_int),
                 ('cout', c_int), ('cout_padded', c_int), ('epilogue', c_int), ('out', c_ptr), ('out_cpitch', c_int),
-                ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr)]
+                ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr), ('a_out', c_ptr), ('a_out_cpitch', c_int)]
 
 
 class Wgrad3x3Args(ctypes.Structure):
-    _fields_ = [('act', ConvSrc * 2), ('nact', c_int), ('dz', c_ptr), ('dz_channels', c_int), ('dz_cpitch', c_int),
-                ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
+    _fields_ = [('act', c_ptr), ('act_channels', c_int), ('act_cpitch', c_int), ('act_coff', c_int), ('dz', c_ptr),
+                ('dz_channels', c_int), ('dz_cpitch', c_int), ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
                 ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int)]
 
 

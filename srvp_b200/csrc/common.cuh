@@ -70,12 +70,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
+  int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("srvp: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+    if (++polls > 16) {  // long wait (e.g. epilogue warps during the main loop): stop competing for issue slots
+      __nanosleep(polls > 256 ? 512 : 64);
+      if (clock64() - t0 > 4000000000LL) {  // ~2 s
+        printf("srvp: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
+}
+
+// Ampere-style asynchronous 16-byte copy global -> shared (SASS: LDGSTS); src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// The mbarrier receives one arrival from this thread once all of its prior cp.async copies have landed.
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
@@ -170,6 +183,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 // ----------------------------------------------------------------------------------------------
 // activations
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : 0.2f * v; }
+__device__ __forceinline__ float lrelu(float v) { return fmaxf(v, 0.2f * v); }
 
 }  // namespace srvp

@@ -45,6 +45,8 @@ struct ConvDev {
   int out_cpitch, out_coff;
   float* stats_partial;
   float* out_f32;
+  __nv_bfloat16* a_out;  // optional copy of the transformed conv input (for the weight-gradient kernel)
+  int a_out_cpitch;
 };
 
 template <int NB, int MT, int KCH, int TPS, int EPI>
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mtile = tile / p.num_nblk;
       const long long vbase = (long long)mtile * MT - p.Wp - 1;
+      const bool store_a = p.a_out != nullptr && (tile % p.num_nblk) == 0;
       for (int s = 0; s < p.nstages; ++s, ++it) {
         const int hs = it % kHaloStages;
         const bool second = s >= p.stages0;
@@ -146,6 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               uint4 a = max8(max8(transform8(r00, scj, shj, sd.lrelu), transform8(r01, scj, shj, sd.lrelu)),
                              max8(transform8(r10, scj, shj, sd.lrelu), transform8(r11, scj, shj, sd.lrelu)));
               *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = a;
+              if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
+                *reinterpret_cast<uint4*>(p.a_out + ((size_t)(f * p.H + y) * p.W + x) * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
             }
           } else {
             const __nv_bfloat16* base;
@@ -157,10 +162,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             uint4 raw[KCH];
 #pragma unroll
             for (int j = 0; j < KCH; ++j) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + j * 8));
+            const bool own = store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT;
+            __nv_bfloat16* adst = p.a_out + ((size_t)(f * p.H + y) * p.W + x) * p.a_out_cpitch + s * KCH * 8;
 #pragma unroll
             for (int j = 0; j < KCH; ++j) {
-              *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) =
-                  transform8(raw[j], sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr, sd.lrelu);
+              const uint4 a = transform8(raw[j], sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr, sd.lrelu);
+              *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = a;
+              if (own) *reinterpret_cast<uint4*>(adst + j * 8) = a;
             }
           }
         }
@@ -449,6 +457,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.wpack = reinterpret_cast<const __nv_bfloat16*>(a->wpack);
   d.F = a->frames; d.H = a->H; d.W = a->W; d.Hp = a->H + 1; d.Wp = a->W + 2;
   d.vtotal = (long long)d.F * d.Hp * d.Wp;
+  SRVP_REQUIRE(d.vtotal < 2000000000LL, "conv3x3: problem too large for 32-bit pixel indices");
   d.cout = a->cout;
   d.num_nblk = a->cout_padded / ch.NB;
   d.num_mtiles = (int)((d.vtotal + ch.MT - 1) / ch.MT);
@@ -457,6 +466,9 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.out_cpitch = a->out_cpitch; d.out_coff = a->out_coff;
   d.stats_partial = a->stats_partial;
   d.out_f32 = a->out_f32_nchw;
+  d.a_out = reinterpret_cast<__nv_bfloat16*>(a->a_out);
+  d.a_out_cpitch = a->a_out_cpitch;
+  if (a->a_out) SRVP_REQUIRE(a->a_out_cpitch % 8 == 0 && a->a_out_cpitch >= nst * kper, "conv3x3: a_out pitch %d too small", a->a_out_cpitch);
   const int sms = num_sms_cached();
   if (a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32) {
     SRVP_REQUIRE(ch.NB == 16 && kper == 64 && a->out_f32_nchw != nullptr, "conv3x3: sigmoid epilogue needs cout<=16, 64-channel stages");

@@ -48,12 +48,14 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
 
 
 // Decodes a virtual pixel index (see conv3x3.cu) into (frame, y, x); returns false for pad positions.
-__device__ __forceinline__ bool decode_vpix(long long v, long long vtotal, int HpWp, int Wp, int H, int W, int& f, int& y, int& x) {
-  if (v < 0 || v >= vtotal) return false;
-  f = (int)(v / HpWp);
-  const int rem = (int)(v - (long long)f * HpWp);
-  y = rem / Wp;
-  x = rem - y * Wp;
+// (32-bit arithmetic: the host checks that the virtual pixel count fits in an int.)
+__device__ __forceinline__ bool decode_vpix(long long v64, long long vtotal, int HpWp, int Wp, int H, int W, int& f, int& y, int& x) {
+  if (v64 < 0 || v64 >= vtotal) return false;
+  const unsigned v = (unsigned)v64;
+  f = (int)(v / (unsigned)HpWp);
+  const unsigned rem = v - (unsigned)f * (unsigned)HpWp;
+  y = (int)(rem / (unsigned)Wp);
+  x = (int)(rem - (unsigned)y * (unsigned)Wp);
   return (y < H) && (x < W);
 }
 

@@ -8,31 +8,35 @@
 // [chunk of 8 channels][pixel][8] shared-memory layout of conv3x3.cu a tile of PT pixels x C channels is
 // directly a SWIZZLE_NONE MN-major UMMA operand (8 pixels x 8 channels = one 128-B core matrix), and a 3x3
 // tap is again only a start-address offset of (ky*Wp + kx) * 16 B on the operand staged with a halo.
-// `a` is never materialised: the loader recomputes it from the raw conv output of the previous layer
-// (BN scale/shift, LeakyReLU, max-pool / upsample, skip concat), exactly like the forward loader.
+// `a` (BN + LeakyReLU + pool/upsample/concat of the previous layer's raw output) is the copy the FORWARD conv loader
+// writes out as a side effect (srvp_conv3x3_args.a_out), so both operands here are plain NHWC bf16 tensors and every
+// global->shared transfer is an asynchronous 16-byte copy (cp.async / LDGSTS) that no thread waits for.
 //
 // One CTA owns a (128-channel M block) x (NBc-channel N block) x (pixel range) piece of the problem and keeps
 // all 9 taps' accumulators in TMEM (9 * NBc fp32 columns), looping over its pixel range in steps of 128
 // pixels. Split-K partial results are added into the fp32 gradient with red.global.add.f32.
 // Either operand can sit on the M side (`halo_on_m`), so that layers with 64 output channels still fill M.
 #include "common.cuh"
-#include "conv_common.cuh"
 #include "../../include/srvp_b200.h"
 
 namespace srvp {
 
 namespace {
 
-constexpr int kWgThreads = 288;  // warps 0-3 epilogue, 4-7 loaders, 8 MMA issuer
+constexpr int kWgThreads = 704;  // warps 0-3 epilogue, 4-19 asynchronous-copy issuers, 20-21 MMA issuers
+constexpr int kCopyThreads = 512;
 constexpr int PT = 128;          // pixels (GEMM-K) per pipeline stage
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;
+constexpr int kSlots = 3;        // copy items per thread and operand (halo tile on the M side: up to 3)
+
+struct PlainDev {
+  const __nv_bfloat16* ptr;
+  int channels, cpitch, coff;
+};
 
 struct WgradDev {
-  SrcDev act[2];     // fused activation sources (the halo operand), concatenated along channels
-  int nact;
-  int act_channels;  // total (padded) channels of the concat
-  SrcDev dz;         // gradient w.r.t. the raw conv output (plain bf16 NHWC)
-  int dz_channels;   // padded
+  PlainDev act;      // materialised conv input a (written by the forward conv loader), the operand staged with a halo
+  PlainDev dz;       // gradient w.r.t. the raw conv output
   int halo_on_m;     // 1: activations on the M side (128-block), dz on the N side
   int m_real, n_real;
   int num_mblk, num_nblk, splits;
@@ -43,31 +47,52 @@ struct WgradDev {
   long long stride_m, stride_n;
   int flip;
   int PH;            // rows of the halo operand tile = PT + 2*Wp + 2
+  int nstg;          // pipeline stages (2..4, as many as fit in shared memory)
+  int dbg;           // development only: 1 = skip loads, 2 = skip MMAs
 };
 
-// Loads `nchunks` 8-channel chunks starting at concat channel c0 for one logical pixel into tile column `r`.
-__device__ __forceinline__ void load_act_row(const WgradDev& p, uint8_t* tile, int rows, int r, int nchunks, int c0, bool valid, int f, int y,
-                                             int x) {
-  for (int j = 0; j < nchunks; ++j) {
-    uint4 val = make_uint4(0, 0, 0, 0);
-    const int c = c0 + j * 8;
-    if (valid && c < p.act_channels) {
-      const int c_first = p.act[0].channels;
-      if (c < c_first) val = load_src8(p.act[0], f, y, x, p.H, p.W, c);
-      else if (p.nact > 1) val = load_src8(p.act[1], f, y, x, p.H, p.W, c - c_first);
-    }
-    *reinterpret_cast<uint4*>(tile + ((size_t)j * rows + r) * 16) = val;
+// One copy item = 4 (or CH) consecutive 16-byte chunks of one pixel row of a tile. A thread keeps the (frame, y, x)
+// position of its items and advances it by PT virtual pixels per pipeline step: no divisions in the steady state.
+struct RowPos {
+  int f, y, x;      // y may be -1.. for rows before the first frame (f < 0 marks "before the tensor")
+  int row, grp;     // tile row and chunk group of this item; row < 0: slot unused
+};
+
+__device__ __forceinline__ void rowpos_init(RowPos& rp, long long v, int HpWp, int Wp) {
+  if (v < 0) {  // only the first halo rows of the very first step: mark invalid but keep advancing consistently
+    const long long vv = v + (long long)HpWp;  // shift by one virtual frame
+    rp.f = -1;
+    rp.y = (int)(vv / Wp);
+    rp.x = (int)(vv - (long long)rp.y * Wp);
+  } else {
+    const unsigned u = (unsigned)v;
+    rp.f = (int)(u / (unsigned)HpWp);
+    const unsigned rem = u - (unsigned)rp.f * (unsigned)HpWp;
+    rp.y = (int)(rem / (unsigned)Wp);
+    rp.x = (int)(rem - (unsigned)rp.y * (unsigned)Wp);
   }
 }
 
-__device__ __forceinline__ void load_dz_row(const WgradDev& p, uint8_t* tile, int rows, int r, int nchunks, int c0, bool valid, int f, int y,
-                                            int x) {
-  const __nv_bfloat16* base = p.dz.ptr + (((size_t)f * p.H + y) * p.W + x) * p.dz.cpitch + p.dz.coff;
-  for (int j = 0; j < nchunks; ++j) {
-    uint4 val = make_uint4(0, 0, 0, 0);
-    const int c = c0 + j * 8;
-    if (valid && c < p.dz_channels) val = __ldg(reinterpret_cast<const uint4*>(base + c));
-    *reinterpret_cast<uint4*>(tile + ((size_t)j * rows + r) * 16) = val;
+__device__ __forceinline__ void rowpos_advance(RowPos& rp, int df, int dy, int dx, int Hp, int Wp) {
+  rp.x += dx;
+  const int cx = rp.x >= Wp;
+  rp.x -= cx * Wp;
+  rp.y += dy + cx;
+  const int cy = rp.y >= Hp;
+  rp.y -= cy * Hp;
+  rp.f += df + cy;
+}
+
+template <int G>
+__device__ __forceinline__ void copy_item(const PlainDev& t, const WgradDev& p, uint8_t* tile, int rows, const RowPos& rp, int c0) {
+  const bool valid = (rp.f >= 0) && (rp.f < p.F) && (rp.y < p.H) && (rp.x < p.W);
+  const int cfirst = c0 + rp.grp * G * 8;
+  const __nv_bfloat16* base = valid ? t.ptr + (((size_t)rp.f * p.H + rp.y) * p.W + rp.x) * t.cpitch + t.coff + cfirst : t.ptr;
+  uint8_t* dst = tile + ((size_t)(rp.grp * G) * rows + rp.row) * 16;
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const bool ok = valid && (cfirst + j * 8 < t.channels);
+    cp_async16(dst + (size_t)j * rows * 16, ok ? base + j * 8 : t.ptr, ok ? 16u : 0u);
   }
 }
 
@@ -75,6 +100,7 @@ template <int NBc>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev p) {
   constexpr int MCH = 16;        // chunks of the M operand (128 channels)
   constexpr int NCH = NBc / 8;   // chunks of the N operand
+  constexpr int GM = 4, GN = NCH < 4 ? NCH : 4;
   constexpr int ACC_COLS = 9 * NBc;
   constexpr int TMEM_COLS = ACC_COLS <= 256 ? 256 : 512;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -83,16 +109,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
   const int n_rows = p.halo_on_m ? PT : PH;
   const size_t m_bytes = (size_t)MCH * m_rows * 16, n_bytes = (size_t)NCH * n_rows * 16;
   const size_t stage_bytes = m_bytes + n_bytes;
+  const int kStages = p.nstg;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
-  uint64_t* full = bars;              // [kStages]
-  uint64_t* empty = bars + kStages;   // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* full = bars;                 // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;   // [kMaxStages]
+  uint64_t* acc_full = bars + 2 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCopyThreads); mbar_init(&empty[i], 2); }
+    mbar_init(acc_full, 2);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -111,52 +138,71 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
   const int nsteps = max(0, step1 - step0);
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ loaders
+  if (warp >= 4 && warp < 20) {
+    // ------------------------------------------------------------------ asynchronous copies (cp.async, zero-fill for pads)
     const int lt = tid - 128;
-    const int mc0 = mblk * 128, nc0 = nblk * NBc;
+    const PlainDev& mop = p.halo_on_m ? p.act : p.dz;
+    const PlainDev& nop = p.halo_on_m ? p.dz : p.act;
+    const int m_c0 = mblk * 128, n_c0 = nblk * NBc;
+    const long long vm = (long long)step0 * PT - (p.halo_on_m ? p.Wp + 1 : 0);
+    const long long vn = (long long)step0 * PT - (p.halo_on_m ? 0 : p.Wp + 1);
+    RowPos ms[kSlots], ns;
+    const int m_items = m_rows * (MCH / GM), n_items = n_rows * (NCH / GN);
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+      const int it = lt + k * kCopyThreads;
+      ms[k].row = -1;
+      if (it < m_items) {
+        ms[k].grp = it / m_rows;
+        ms[k].row = it - ms[k].grp * m_rows;
+        rowpos_init(ms[k], vm + ms[k].row, HpWp, p.Wp);
+      }
+    }
+    ns.row = -1;
+    if (lt < n_items) {
+      ns.grp = lt / n_rows;
+      ns.row = lt - ns.grp * n_rows;
+      rowpos_init(ns, vn + ns.row, HpWp, p.Wp);
+    }
+    const int df = PT / HpWp, dy = (PT % HpWp) / p.Wp, dx = (PT % HpWp) % p.Wp;
     for (int i = 0; i < nsteps; ++i) {
       const int st = i % kStages;
       mbar_wait(&empty[st], ((i / kStages) & 1) ^ 1);
       uint8_t* mt = smem + st * stage_bytes;
       uint8_t* nt = mt + m_bytes;
-      const long long v0 = (long long)(step0 + i) * PT;
-      // plain (dz) operand: PT rows; halo (activation) operand: PH rows starting at v0 - Wp - 1
-      for (int r = lt; r < PT; r += 128) {
-        int f = 0, y = 0, x = 0;
-        const bool valid = decode_vpix(v0 + r, p.vtotal, HpWp, p.Wp, p.H, p.W, f, y, x);
-        if (p.halo_on_m) load_dz_row(p, nt, PT, r, NCH, nc0, valid, f, y, x);
-        else load_dz_row(p, mt, PT, r, MCH, mc0, valid, f, y, x);
+      if ((p.dbg & 3) != 1) {
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k)
+          if (ms[k].row >= 0) copy_item<GM>(mop, p, mt, m_rows, ms[k], m_c0);
+        if (ns.row >= 0) copy_item<GN>(nop, p, nt, n_rows, ns, n_c0);
       }
-      for (int r = lt; r < PH; r += 128) {
-        int f = 0, y = 0, x = 0;
-        const bool valid = decode_vpix(v0 - p.Wp - 1 + r, p.vtotal, HpWp, p.Wp, p.H, p.W, f, y, x);
-        if (p.halo_on_m) load_act_row(p, mt, PH, r, MCH, mc0, valid, f, y, x);
-        else load_act_row(p, nt, PH, r, NCH, nc0, valid, f, y, x);
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&full[st]);
+      cp_async_arrive_noinc(&full[st]);
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) rowpos_advance(ms[k], df, dy, dx, p.Hp, p.Wp);
+      rowpos_advance(ns, df, dy, dx, p.Hp, p.Wp);
     }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp >= 20) {
+    // ------------------------------------------------------------------ MMA issuers: warp 20 -> taps 0-4, warp 21 -> taps 5-8
+    // (one thread sustains ~1 MMA / 50 cycles, the tensor core accepts one small-N MMA per 40: two issuers close the gap)
     if (lane == 0 && nsteps > 0) {
+      const int tap_lo = warp == 20 ? 0 : 5, tap_hi = warp == 20 ? 5 : 9;
       constexpr uint32_t idesc = umma_idesc_bf16(128, NBc, 1, 1);
       const uint32_t base = smem_u32(smem);
       for (int i = 0; i < nsteps; ++i) {
         const int st = i % kStages;
         mbar_wait(&full[st], (i / kStages) & 1);
+        if (!(p.dbg & 4)) fence_proxy_async_smem();  // cp.async (generic proxy) writes of the copy warps -> visible to the UMMA (async proxy) reads
         tc_fence_after();
         const uint32_t ma = base + st * stage_bytes, na = ma + m_bytes;
+        const uint64_t ad0 = umma_desc(ma, 128, m_rows * 16), bd0 = umma_desc(na, 128, n_rows * 16);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int ky = tap / 3, kx = tap - 3 * ky;
-          const uint32_t shift = (ky * p.Wp + kx) * 16;
-          const uint32_t a0 = ma + (p.halo_on_m ? shift : 0), b0 = na + (p.halo_on_m ? 0 : shift);
+          const uint32_t shift = (uint32_t)(ky * p.Wp + kx);  // in 16-byte units = descriptor address units
+          const uint64_t ad = ad0 + (p.halo_on_m ? shift : 0u), bd = bd0 + (p.halo_on_m ? 0u : shift);
 #pragma unroll
           for (int kk = 0; kk < PT / 16; ++kk) {
-            const uint64_t ad = umma_desc(a0 + kk * 256, 128, m_rows * 16);
-            const uint64_t bd = umma_desc(b0 + kk * 256, 128, n_rows * 16);
-            umma_bf16(tmem_base + tap * NBc, ad, bd, idesc, (i | kk) != 0);
+            if ((p.dbg & 3) != 2) umma_bf16(tmem_base + tap * NBc, ad + kk * 16, bd + kk * 16, idesc, (i | kk) != 0);
           }
         }
         umma_commit(&empty[st]);
@@ -202,28 +248,21 @@ using namespace srvp;
 
 extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SRVP_REQUIRE(a != nullptr && a->dw != nullptr && a->dz != nullptr, "wgrad3x3: null argument");
-  SRVP_REQUIRE(a->nact == 1 || a->nact == 2, "wgrad3x3: nact must be 1 or 2");
-  WgradDev d{};
-  d.nact = a->nact;
-  int ctot = 0;
-  for (int i = 0; i < a->nact; ++i) {
-    const srvp_conv_src& s = a->act[i];
-    SRVP_REQUIRE(s.ptr != nullptr && s.channels % 8 == 0 && s.cpitch % 8 == 0 && s.coff % 8 == 0, "wgrad3x3: bad activation source %d", i);
-    SRVP_REQUIRE((s.scale == nullptr) == (s.shift == nullptr), "wgrad3x3: scale and shift must both be given");
-    d.act[i] = SrcDev{reinterpret_cast<const __nv_bfloat16*>(s.ptr), s.scale, s.shift, s.frame_map, s.channels, s.cpitch, s.coff, s.mode, s.lrelu};
-    ctot += s.channels;
-  }
-  d.act_channels = ctot;
+  SRVP_REQUIRE(a != nullptr && a->dw != nullptr && a->dz != nullptr && a->act != nullptr, "wgrad3x3: null argument");
+  SRVP_REQUIRE(a->act_channels % 8 == 0 && a->act_cpitch % 8 == 0 && a->act_coff % 8 == 0, "wgrad3x3: bad activation layout");
   SRVP_REQUIRE(a->dz_channels % 8 == 0 && a->dz_cpitch % 8 == 0 && a->dz_coff % 8 == 0, "wgrad3x3: bad dz layout");
-  d.dz = SrcDev{reinterpret_cast<const __nv_bfloat16*>(a->dz), nullptr, nullptr, nullptr, a->dz_channels, a->dz_cpitch, a->dz_coff, 0, 0};
-  d.dz_channels = a->dz_channels;
+  WgradDev d{};
+  d.act = PlainDev{reinterpret_cast<const __nv_bfloat16*>(a->act), a->act_channels, a->act_cpitch, a->act_coff};
+  d.dz = PlainDev{reinterpret_cast<const __nv_bfloat16*>(a->dz), a->dz_channels, a->dz_cpitch, a->dz_coff};
+  const int ctot = a->act_channels;
   d.F = a->frames; d.H = a->H; d.W = a->W; d.Hp = a->H + 1; d.Wp = a->W + 2;
   d.vtotal = (long long)d.F * d.Hp * d.Wp;
+  SRVP_REQUIRE(d.vtotal < 2000000000LL, "wgrad3x3: problem too large for 32-bit pixel indices");
   d.steps_total = (int)((d.vtotal + PT - 1) / PT);
   d.PH = PT + 2 * d.Wp + 2;
   d.dw = a->dw;
-  d.flip = a->flip;
+  d.flip = a->flip & 1;
+  d.dbg = a->flip >> 8;
   // which operand fills the 128-wide M side
   const int cout_real = a->cout, cin_real = a->cin;
   d.halo_on_m = (a->dz_channels < 128 && ctot >= 128) ? 1 : 0;
@@ -246,7 +285,14 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   if (splits > d.steps_total) splits = d.steps_total;
   d.splits = splits;
   const size_t m_rows = d.halo_on_m ? d.PH : PT, n_rows = d.halo_on_m ? PT : d.PH;
-  size_t smem = kStages * ((size_t)16 * m_rows * 16 + (size_t)(NBc / 8) * n_rows * 16) + 16 * 8 + 16;
+  SRVP_REQUIRE((int)(m_rows * 4) <= kSlots * kCopyThreads, "wgrad3x3: M tile has too many copy items (W=%d)", a->W);
+  SRVP_REQUIRE((int)(n_rows * ((NBc / 8) < 4 ? 1 : (NBc / 8) / 4)) <= kCopyThreads, "wgrad3x3: N tile has too many copy items (W=%d)", a->W);
+  const size_t stage_bytes = (size_t)16 * m_rows * 16 + (size_t)(NBc / 8) * n_rows * 16;
+  int nstg = (int)((227 * 1024 - 256) / stage_bytes);
+  if (nstg > kMaxStages) nstg = kMaxStages;
+  SRVP_REQUIRE(nstg >= 2, "wgrad3x3: tile too large for shared memory (W=%d)", a->W);
+  d.nstg = nstg;
+  size_t smem = nstg * stage_bytes + 16 * 8 + 16;
   if (smem < 120 * 1024) smem = 120 * 1024;
   SRVP_REQUIRE(smem <= 227 * 1024, "wgrad3x3: shared memory %zu B exceeds 227 KB", smem);
   const int grid = pairs * splits;

@@ -108,14 +108,16 @@ def _encoder_fwd(enc, x, training, want_stats_update=True):
         src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, blk.in_mode, prev.lrelu)
         wp = ops.pack_conv3x3(blk.conv.weight, 'conv')
         st = BNState(blk.cout, dev)
-        z, partial = ops.conv3x3([src], wp, F_, blk.res, blk.res, blk.cout, stats=training, cin_real=blk.cin)
+        save = training and src.tensor is not c.x16   # the weight-gradient kernel reads the loader's copy of the conv input
+        r = ops.conv3x3([src], wp, F_, blk.res, blk.res, blk.cout, stats=training, cin_real=blk.cin, save_input=save)
+        z, partial = r[0], r[1]
         if training:
             ops.bn_finalize(partial, float(F_ * blk.res * blk.res), blk.bn, st, training_update=want_stats_update)
         else:
             ops.bn_eval_params(blk.bn, st)
         c.z.append(z)
         c.st.append(st)
-        c.srcs.append(src)
+        c.srcs.append(r[2] if save else c.x16)
         prev = Src(z, blk.cout, st.scale, st.shift, None, 0, SRC_DIRECT, True)
     # last_conv: pool -> 4x4 valid conv (a GEMM over (y, x, c)) -> BN -> tanh
     last = enc.last_conv[-1]
@@ -160,7 +162,7 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[3 * li + 1], grads[3 * li + 2], da, da_mode, F_, blk.res, blk.res,
                         blk.cout, **kw)
         cin_real = blk.cin
-        ops.wgrad3x3([c.srcs[li]], dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_real, grads[3 * li], 'conv')
+        ops.wgrad3x3(c.srcs[li], c.srcs[li].shape[-1], dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_real, grads[3 * li], 'conv')
         if li > 0:
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, blk.cin)
@@ -241,19 +243,24 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
             srcs.append(_skip_src(skip_levels[blk.skip_level], frame_map))
         wp = ops.pack_conv3x3(blk.conv.weight, 'conv')
         st = BNState(blk.cout, dev)
-        z, partial = ops.conv3x3(srcs, wp, F_, blk.res, blk.res, blk.cout, stats=training)
+        r = ops.conv3x3(srcs, wp, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training)
+        z, partial = r[0], r[1]
         if training:
             ops.bn_finalize(partial, float(F_ * blk.res * blk.res), blk.bn, st, training_update=want_stats_update)
         else:
             ops.bn_eval_params(blk.bn, st)
         c.z.append(z)
         c.st.append(st)
-        c.srcs.append(srcs)
+        c.srcs.append(r[2] if training else None)
+        c.skip_c0 = getattr(c, 'skip_c0', {})
+        c.skip_c0[len(c.z) - 1] = srcs[0].channels
         prev = Src(z, blk.cout, st.scale, st.shift, None, 0, SRC_DIRECT, True)
     final = dec.conv[3][1]
     c.final_src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, SRC_DIRECT, True)
     wp = ops.pack_conv3x3(final.weight, 'convT')
-    c.x_hat, _ = ops.conv3x3([c.final_src], wp, F_, 64, 64, final.out_channels, sigmoid_nchw=True)
+    r = ops.conv3x3([c.final_src], wp, F_, 64, 64, final.out_channels, sigmoid_nchw=True, save_input=training)
+    c.x_hat = r[0]
+    c.final_a = r[2] if training else None
     if training and want_stats_update:
         torch._foreach_add_([b.num_batches_tracked for b in _bn_list(dec)], 1)
     return c.x_hat, c
@@ -268,7 +275,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     final = dec.conv[3][1]
     nc = final.out_channels
     dz = ops.sigmoid_bwd(d_xhat.contiguous(), c.x_hat)  # (F,64,64,16)
-    ops.wgrad3x3([c.final_src], dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT')
+    ops.wgrad3x3(c.final_a, final.in_channels, dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT')
     wp = ops.pack_conv3x3(final.weight, 'convT_dgrad')
     da, _ = ops.conv3x3([Src(dz, 16)], wp, F_, 64, 64, final.in_channels, cin_real=nc)
     da_mode, da_coff = SRC_DIRECT, 0
@@ -278,13 +285,13 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
         gi = 3 + 3 * li
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[gi + 1], grads[gi + 2], da, da_mode, F_, blk.res, blk.res, blk.cout,
                         da_coff=da_coff)
-        cin_tot = sum(s.channels for s in c.srcs[li])
-        ops.wgrad3x3(c.srcs[li], dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv')
+        cin_tot = c.srcs[li].shape[-1]
+        ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv')
         wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
         da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, cin_tot)
         da_mode, da_coff = blk.in_mode, 0
         if blk.skip_level is not None:
-            skip_grads[blk.skip_level] = (da, c.srcs[li][0].channels)
+            skip_grads[blk.skip_level] = (da, c.skip_c0[li])
     if skip_handle is not None and skip_grads:
         skip_handle.grads = [skip_grads[i] for i in range(len(skip_grads))]
     # first_upconv backward

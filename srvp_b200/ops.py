@@ -125,13 +125,14 @@ def _fill_src(cs, s):
 
 
 @profiled('wgrad3x3')
-def wgrad3x3(srcs, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0):
-    """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'."""
+def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0):
+    """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
+
+    act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...)."""
     a = _lib.Wgrad3x3Args()
-    a.nact = len(srcs)
-    for i, s in enumerate(srcs):
-        _fill_src(a.act[i], s)
-    assert dz.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert act.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    a.act = ptr(act)
+    a.act_channels, a.act_cpitch, a.act_coff = act_channels, act.shape[-1], act_coff
     a.dz = ptr(dz)
     a.dz_channels, a.dz_cpitch, a.dz_coff = dz_channels, dz.shape[-1], dz_coff
     a.frames, a.H, a.W = frames, H, W
@@ -147,7 +148,8 @@ def wgrad3x3(srcs, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0
 
 
 @profiled('conv3x3')
-def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None):
+def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None,
+            save_input=False):
     """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None)."""
     a = _lib.Conv3x3Args()
     a.nsrc = len(srcs)
@@ -188,10 +190,16 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
             nmt = lib().srvp_conv3x3_num_mtiles(c_int(frames), c_int(H), c_int(W), c_int(cout_padded), c_int(kper))
             stats_partial = torch.empty(nmt, cout, 2, dtype=torch.float32, device=dev)
             a.stats_partial = ptr(stats_partial)
+    a_out = None
+    if save_input:
+        a_out = torch.empty(frames, H, W, sum(s.channels for s in srcs), dtype=torch.bfloat16, device=dev)
+        a.a_out, a.a_out_cpitch = ptr(a_out), a_out.shape[-1]
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
     cin_real = cin_real if cin_real is not None else sum(s.channels for s in srcs)
     obytes = out.numel() * out.element_size()
     _account(2.0 * frames * H * W * cout * cin_real * 9, sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
+    if save_input:
+        return out, stats_partial, a_out
     return out, stats_partial
 
 
