@@ -38,34 +38,45 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU through NVML (in-process, initialised before the timed region)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
-        self.max_mhz, self.reasons = None, set()
+        self.samples, self.stop_flag, self.max_mhz, self.reasons = [], False, None, set()
+        self.nv, self.h = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            phys = index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                phys = int(vis.split(',')[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
-        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        if self.nv is None:
+            return
+        nv = self.nv
+        masks = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown, 'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown, 'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [v.strip() for v in out.split(',')]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith('active'):
-                        self.reasons.add(n)
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, m in masks.items():
+                    if r & m:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         s = sorted(self.samples)
-        return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+        return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(s))
 
 
 def elbo_loss(out, x):

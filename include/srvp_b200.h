@@ -64,14 +64,14 @@ typedef struct {
   int32_t epilogue;       /* SRVP_EPI_* */
   srvp_bf16* out;         /* EPI_RAW_BF16: NHWC, channel pitch out_cpitch, first channel out_coff */
   int32_t out_cpitch, out_coff;
-  float* stats_partial;   /* optional [num_mtiles][cout][2] per-tile (sum, sum of squares) of the stored bf16 values */
+  float* stats_partial;   /* optional [srvp_conv3x3_num_mtiles()][cout][2]: per-CTA (sum, sum of squares) of the stored bf16 values */
   float* out_f32_nchw;    /* EPI_SIGMOID_NCHW_F32: (frames, cout, H, W) fp32 */
   srvp_bf16* a_out;       /* optional: the loader also stores the conv input it computed (BN+LReLU+pool/upsample/concat applied),
                              NHWC (frames,H,W,a_out_cpitch); the weight-gradient kernel reads it back */
   int32_t a_out_cpitch;
 } srvp_conv3x3_args;
 
-/* Number of M tiles (rows of stats_partial) srvp_conv3x3 will use for this geometry / channel count. */
+/* Number of rows of stats_partial srvp_conv3x3 writes for this geometry / channel count (= its persistent grid size). */
 int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kchannels_per_stage);
 /* N block the kernel uses for a padded output-channel count (16, 64, 128 or 256). */
 int srvp_conv3x3_nblock(int32_t cout_padded);
@@ -129,9 +129,10 @@ int srvp_channel_stats_rows(int64_t rows);
 int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, float* partial /* [srvp_channel_stats_rows(rows)][C][2] */, void* stream);
 
 /* Backward of conv -> BN(train) -> LeakyReLU [-> MaxPool2d(2) | Upsample(2)] (autograd of conv.py:101-107, :204, :331).
- * reduce:   g = lrelu'(bn(z)) * (da routed through pool/upsample + skip-connection gradient), partial sums of (g, g*xhat)
+ * With g = lrelu'(bn(z)) * (da routed through pool/upsample + skip-connection gradient), recomputed by both passes:
+ * reduce:   per-block partial sums of (g, g*xhat)
  * finalize: c1 = mean(g), c2 = mean(g*xhat); dgamma += sum(g*xhat); dbeta += sum(g)
- * apply:    dz = gamma*invstd*(g - c1 - xhat*c2), in place on g. */
+ * apply:    dz = gamma*invstd*(g - c1 - xhat*c2) written to args->g. */
 typedef struct {
   const srvp_bf16* z;     /* raw conv output of this layer (frames,H,W,C) */
   const float* scale;     /* forward affine of this layer */
@@ -143,8 +144,8 @@ typedef struct {
   const srvp_bf16* skip;  /* optional: gradient from the decoder's skip input (nt*B, H, W, skip_cpitch), summed over nt */
   int32_t skip_cpitch, skip_coff, nt, B;
   const int32_t* inv_map; /* (frames): video index b if this frame was selected as skip frame (srvp.py:185-187), else -1 */
-  srvp_bf16* g;           /* out (frames,H,W,C) */
-  float* partial;         /* out [srvp_bn_bwd_reduce_rows(...)][C][2] */
+  srvp_bf16* g;           /* apply: out dz (frames,H,W,C) */
+  float* partial;         /* reduce: out [srvp_bn_bwd_reduce_rows(...)][C][2] */
   int32_t frames, H, W, C;
   int32_t lrelu;
 } srvp_bn_bwd_args;
@@ -152,8 +153,7 @@ int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t da_mod
 int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* args, void* stream);
 int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,
                          void* stream);
-int srvp_bn_bwd_apply(srvp_bf16* g_inout, const srvp_bf16* z, const float* gamma, const float* mean, const float* invstd, const float* c1,
-                      const float* c2, int64_t positions, int32_t C, void* stream);
+int srvp_bn_bwd_apply(const srvp_bn_bwd_args* args, const float* gamma, const float* c1, const float* c2, void* stream);
 /* encoder.last_conv's BatchNorm2d + Tanh on a (rows = T*B, C = nhx) fp32 matrix (conv.py:179, :221-224), forward and backward.
  * training != 0: batch statistics (saved to mean/invstd, affine written to scale/shift, running stats updated when given);
  * training == 0: scale/shift are inputs (srvp_bn_eval_params). */

@@ -49,6 +49,22 @@ struct ConvDev {
   int a_out_cpitch;
 };
 
+// Column sums across the 32 lanes of a warp by recursive halving: lane l ends up with sum over lanes of v[l].
+// 31 shuffles for 32 columns (a plain butterfly per column would need 160).
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
 template <int NB, int MT, int KCH, int TPS, int EPI>
 struct Cfg {
   static constexpr int MBLK = MT / 128;
@@ -61,7 +77,7 @@ struct Cfg {
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(9 % TPS == 0, "taps per slot must divide 9");
   static size_t smem_bytes(int P) {
-    return (size_t)kHaloStages * KCH * P * 16 + (size_t)WSLOTS * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 64 * 8 + 16;
+    return (size_t)kHaloStages * KCH * P * 16 + (size_t)WSLOTS * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 2 * NB * 2 * 4 + 64 * 8 + 16;
   }
 };
 
@@ -74,7 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   uint8_t* wslots = halo + (size_t)kHaloStages * KCH * P * 16;
   uint8_t* staging = wslots + (size_t)C::WSLOTS * C::SLOT_BYTES;
   int* rowpix = reinterpret_cast<int*>(staging + C::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowpix + 128);
+  float* statbuf = reinterpret_cast<float*>(rowpix + 128);  // [2 N blocks][NB][2]: per-CTA running (sum, sumsq)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(statbuf + 2 * NB * 2);
   uint64_t* halo_full = bars;                    // [kHaloStages]
   uint64_t* halo_empty = bars + kHaloStages;     // [kHaloStages]
   uint64_t* w_full = bars + 2 * kHaloStages;     // [WSLOTS]
@@ -240,6 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3)
+    for (int i = tid; i < 2 * NB * 2; i += 128) statbuf[i] = 0.f;
+    named_bar_sync(1, 128);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mtile = tile / p.num_nblk, nblk = tile % p.num_nblk;
@@ -247,23 +266,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
       mbar_wait(&acc_full[as], (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
-      constexpr int CPT = (NB + 127) / 128;  // stat columns per thread
-      float s1[CPT], s2[CPT];
+      constexpr int NBAT = (NB + 31) / 32;  // 32-column batches; lane l accumulates column batch*32 + l over this warp's rows
+      float s1[NBAT], s2[NBAT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) s1[i] = s2[i] = 0.f;
+      for (int i = 0; i < NBAT; ++i) s1[i] = s2[i] = 0.f;
+      const bool do_stats = p.stats_partial != nullptr;
 
 #pragma unroll 1
       for (int mb = 0; mb < C::MBLK; ++mb) {
         const long long v = (long long)mtile * MT + mb * 128 + tid;
         int f = 0, y = 0, x = 0;
-        bool valid = v < p.vtotal;
-        if (valid) {
-          f = (int)(v / HpWp);
-          const int rem = (int)(v - (long long)f * HpWp);
-          y = rem / p.Wp;
-          x = rem - y * p.Wp;
-          valid = (y < p.H) && (x < p.W);
-        }
+        const bool valid = decode_vpix(v, p.vtotal, HpWp, p.Wp, p.H, p.W, f, y, x);
         if constexpr (EPI == SRVP_EPI_SIGMOID_NCHW_F32) {
           float vals[16];
           tmem_ld16(acc + mb * NB, vals);
@@ -281,51 +294,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             }
           }
         } else {
+          // every warp stages, reduces and stores its own 32 rows: only warp-level synchronisation is needed
           rowpix[tid] = valid ? ((f * p.H + y) * p.W + x) : -1;
           uint8_t* srow = staging + (size_t)tid * C::STAGE_PITCH;
 #pragma unroll
-          for (int c0 = 0; c0 < NB; c0 += 32) {
+          for (int bi = 0; bi < NBAT; ++bi) {
             float vals[32];
-            tmem_ld32(acc + mb * NB + c0, vals);
+            tmem_ld32(acc + mb * NB + bi * 32, vals);
+            uint32_t pk[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16x2(vals[q * 8 + 0], vals[q * 8 + 1]);
-              o.y = pack_bf16x2(vals[q * 8 + 2], vals[q * 8 + 3]);
-              o.z = pack_bf16x2(vals[q * 8 + 4], vals[q * 8 + 5]);
-              o.w = pack_bf16x2(vals[q * 8 + 6], vals[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(srow + c0 * 2 + q * 16) = o;
+            for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(vals[2 * q], vals[2 * q + 1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(srow + bi * 64 + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            if (do_stats) {
+              // statistics of the stored (bf16-rounded) values; pad rows contribute zero
+              float sq[32];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const float2 r = unpack_bf16x2(pk[q]);
+                vals[2 * q] = valid ? r.x : 0.f;
+                vals[2 * q + 1] = valid ? r.y : 0.f;
+                sq[2 * q] = vals[2 * q] * vals[2 * q];
+                sq[2 * q + 1] = vals[2 * q + 1] * vals[2 * q + 1];
+              }
+              s1[bi] += warp_transpose_reduce32(vals, lane);
+              s2[bi] += warp_transpose_reduce32(sq, lane);
             }
           }
           if (mb == C::MBLK - 1) {
             tc_fence_before();
             mbar_arrive(&acc_empty[as]);
           }
-          named_bar_sync(1, 128);
-          // per-channel statistics of the stored (bf16-rounded) values
-          if (p.stats_partial != nullptr) {
-#pragma unroll
-            for (int i = 0; i < CPT; ++i) {
-              const int c = tid + i * 128;
-              if (c < NB) {
-                float a1 = 0.f, a2 = 0.f;
-                for (int r = 0; r < 128; ++r) {
-                  if (rowpix[r] >= 0) {
-                    const float val = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(staging + (size_t)r * C::STAGE_PITCH + c * 2));
-                    a1 += val;
-                    a2 = fmaf(val, val, a2);
-                  }
-                }
-                s1[i] += a1;
-                s2[i] += a2;
-              }
-            }
-          }
+          __syncwarp();
           // coalesced store of the valid rows
           constexpr int LPR = NB / 8;        // lanes per row (16 B each)
           constexpr int RPI = 32 / LPR;      // rows per warp instruction
           const int lrow = lane / LPR, lcol = lane % LPR;
           const int cbase = nblk * NB + lcol * 8;
+#pragma unroll 4
           for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
             const int r = r0 + lrow;
             const int pix = rowpix[r];
@@ -334,20 +341,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
             }
           }
-          named_bar_sync(1, 128);
+          __syncwarp();
         }
       }
       if constexpr (EPI == SRVP_EPI_RAW_BF16) {
-        if (p.stats_partial != nullptr) {
+        if (do_stats) {
+          // add this tile's column sums to the per-CTA accumulators, one warp after the other (fixed order: deterministic)
+          float* wacc = statbuf + ((nblk & 1) * NB) * 2;
+#pragma unroll 1
+          for (int w = 0; w < 4; ++w) {
+            if (warp == w) {
 #pragma unroll
-          for (int i = 0; i < CPT; ++i) {
-            const int c = tid + i * 128;
-            const int cg = nblk * NB + c;
-            if (c < NB && cg < p.cout) {
-              float* dst = p.stats_partial + ((size_t)mtile * p.cout + cg) * 2;
-              dst[0] = s1[i];
-              dst[1] = s2[i];
+              for (int bi = 0; bi < NBAT; ++bi) {
+                wacc[(bi * 32 + lane) * 2 + 0] += s1[bi];
+                wacc[(bi * 32 + lane) * 2 + 1] += s2[bi];
+              }
             }
+            named_bar_sync(1, 128);
+          }
+        }
+      }
+    }
+    if constexpr (EPI == SRVP_EPI_RAW_BF16) {
+      if (p.stats_partial != nullptr) {
+        // one row of partial sums per CTA
+        for (int c = tid; c < p.num_nblk * NB; c += 128) {
+          if (c < p.cout) {
+            float* dst = p.stats_partial + ((size_t)blockIdx.x * p.cout + c) * 2;
+            dst[0] = statbuf[c * 2];
+            dst[1] = statbuf[c * 2 + 1];
           }
         }
       }
@@ -429,7 +451,9 @@ extern "C" int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int
   (void)kchannels_per_stage;
   const Choice c = choose(cout_padded);
   const long long vtotal = (long long)frames * (H + 1) * (W + 2);
-  return (int)((vtotal + c.MT - 1) / c.MT);
+  const long long tiles = ((vtotal + c.MT - 1) / c.MT) * (cout_padded / c.NB);
+  const int sms = num_sms_cached();
+  return (int)(tiles < sms ? tiles : sms);  // = grid size: every persistent CTA emits one row of partial statistics
 }
 
 extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
@@ -465,6 +489,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   d.out_cpitch = a->out_cpitch; d.out_coff = a->out_coff;
   d.stats_partial = a->stats_partial;
+  if (a->stats_partial) SRVP_REQUIRE(d.num_nblk <= 2, "conv3x3: statistics support at most 2 N blocks (cout %d)", a->cout);
   d.out_f32 = a->out_f32_nchw;
   d.a_out = reinterpret_cast<__nv_bfloat16*>(a->a_out);
   d.a_out_cpitch = a->a_out_cpitch;

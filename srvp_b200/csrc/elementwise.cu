@@ -56,26 +56,29 @@ __global__ void materialize_src_kernel(const SrcDev sd, __nv_bfloat16* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ BN forward stats
-// One warp per channel reduces the per-tile partial sums in fp64, then derives the affine and updates running stats.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+// Block = 32 channels x 8 row lanes: coalesced float2 reads of the per-tile partial sums, fp64 accumulation, fixed-order
+// combination in shared memory; then the affine, the saved statistics and the running-stat update.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                                         float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                                         float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  __shared__ double r1[8][32], r2[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int r = lane; r < rows; r += 32) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
-    s1 += v.x;
-    s2 += v.y;
+  if (c < C) {
+    for (int r = rl; r < rows; r += 8) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
+      s1 += v.x;
+      s2 += v.y;
+    }
   }
+  r1[rl][cl] = s1;
+  r2[rl][cl] = s2;
+  __syncthreads();
+  if (rl == 0 && c < C) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane == 0) {
+    for (int k = 1; k < 8; ++k) { s1 += r1[k][cl]; s2 += r2[k][cl]; }
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -147,184 +150,191 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
-// Work item = one 2x2 window (POOL2) or one pixel (otherwise) x 8 channels. Threads of a block share the channel chunk
-// index pattern tid % (C/8), so per-thread register sums are per-channel; they are combined across the block in smem.
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdDev p, long long items, int items_per_block) {
-  __shared__ float red[256 * 17];
+// Work item = one 2x2 window (POOL2) or one pixel (otherwise) x 8 channels. Both passes recompute
+//   g = lrelu'(bn(z)) * (da routed through max-pool arg-max / summed over the 2x2 upsample footprint + skip gradient)
+// from (da, z) so that g itself never goes to HBM:
+//   pass 1 (APPLY = false): per-block partial sums of (g, g * xhat)             reads da, z
+//   pass 2 (APPLY = true) : dz = gamma * invstd * (g - c1 - xhat * c2)          reads da, z; writes dz
+// Threads of a block share the channel-chunk pattern tid % (C/8): register sums are per channel and are combined across the
+// block in shared memory in a fixed order (deterministic).
+__device__ __forceinline__ void add_skip8(const BnBwdDev& p, int b, int y, int x, int c0, float* g) {
+  for (int t = 0; t < p.nt; ++t) {
+    float sk[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.skip + ((((size_t)t * p.B + b) * p.H + y) * p.W + x) * p.skip_cpitch + p.skip_coff + c0)), sk);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] += sk[e];
+  }
+}
+
+// U work items are processed per loop iteration with all their 16-byte loads issued first (memory-level parallelism:
+// this kernel is purely HBM bound); per-channel constants live in registers, folded to the minimum:
+//   sign test   pre = z*sc + sh
+//   reduce      s1 += g,  s2 += g * (z*is - mu_is)
+//   apply       dz = k0*g + z*ka + kb      with k0 = gamma*is, ka = -is*k0*c2, kb = k0*(mu*is*c2 - c1)
+template <int MODE, bool APPLY>
+__global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_kernel(const BnBwdDev p, long long items, int items_per_block, const float* __restrict__ gamma,
+                                                       const float* __restrict__ c1, const float* __restrict__ c2) {
+  __shared__ float red[APPLY ? 1 : 256 * 17];
+  constexpr bool POOLED = MODE == SRVP_SRC_POOL2;
+  constexpr bool UPS = MODE == SRVP_SRC_UP2;
+  constexpr int NQ = POOLED ? 4 : 1;      // z loads per item
+  constexpr int ND = UPS ? 4 : 1;         // da loads per item
+  constexpr int U = POOLED ? 2 : (UPS ? 2 : 4);
   const int cpp = p.C / 8;               // chunks per pixel
   const int tid = threadIdx.x;
   const int j = tid % cpp;               // this thread's channel chunk
   const int lanes = 256 / cpp;           // pixel lanes per block
   const int pl = tid / cpp;
   const int c0 = j * 8;
-  float sc[8], sh[8], mu[8], is[8];
+  float sc[8], sh[8], ka[8], kb[8], k0[8];   // reduce: ka = is, kb = mu*is ; apply: see above
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { sc[e] = p.scale[c0 + e]; sh[e] = p.shift[c0 + e]; mu[e] = p.mean[c0 + e]; is[e] = p.invstd[c0 + e]; }
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = p.scale[c0 + e]; sh[e] = p.shift[c0 + e];
+    const float is = p.invstd[c0 + e], mu = p.mean[c0 + e];
+    if (APPLY) {
+      k0[e] = gamma[c0 + e] * is;
+      ka[e] = -is * k0[e] * c2[c0 + e];
+      kb[e] = k0[e] * (mu * is * c2[c0 + e] - c1[c0 + e]);
+    } else {
+      k0[e] = 0.f; ka[e] = is; kb[e] = mu * is;
+    }
+  }
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-  const bool pooled = p.da_mode == SRVP_SRC_POOL2;
-  const int Hi = pooled ? p.H / 2 : p.H, Wi = pooled ? p.W / 2 : p.W;  // item grid
+  const int Hi = POOLED ? p.H / 2 : p.H, Wi = POOLED ? p.W / 2 : p.W;  // item grid
+  const int Hd = UPS ? p.H * 2 : Hi, Wd = UPS ? p.W * 2 : Wi;          // da grid
   const long long i0 = (long long)blockIdx.x * items_per_block;
   const long long i1 = min(items, i0 + items_per_block);
-  if (pl < lanes) {
-    for (long long it = i0 + pl; it < i1; it += lanes) {
-      const int xi = (int)(it % Wi);
-      const long long t2 = it / Wi;
-      const int yi = (int)(t2 % Hi);
-      const int f = (int)(t2 / Hi);
+  for (long long itb = i0 + pl; itb < i1; itb += (long long)lanes * U) {
+    uint4 dav[U][ND], zvv[U][NQ];
+    int fy[U], yy[U], xx[U];
+    bool act[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long it = itb + (long long)u * lanes;
+      act[u] = it < i1;
+      const long long itc = act[u] ? it : i0;
+      xx[u] = (int)(itc % Wi);
+      const long long t2 = itc / Wi;
+      yy[u] = (int)(t2 % Hi);
+      fy[u] = (int)(t2 / Hi);
+      const __nv_bfloat16* dbase = p.da + (((size_t)fy[u] * Hd + (UPS ? 2 * yy[u] : yy[u])) * Wd + (UPS ? 2 * xx[u] : xx[u])) * p.da_cpitch + p.da_coff + c0;
+      dav[u][0] = __ldg(reinterpret_cast<const uint4*>(dbase));
+      if (UPS) {
+        dav[u][1 % ND] = __ldg(reinterpret_cast<const uint4*>(dbase + p.da_cpitch));
+        dav[u][2 % ND] = __ldg(reinterpret_cast<const uint4*>(dbase + (size_t)Wd * p.da_cpitch));
+        dav[u][3 % ND] = __ldg(reinterpret_cast<const uint4*>(dbase + (size_t)(Wd + 1) * p.da_cpitch));
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int y = POOLED ? 2 * yy[u] + (q >> 1) : yy[u], x = POOLED ? 2 * xx[u] + (q & 1) : xx[u];
+        zvv[u][q] = __ldg(reinterpret_cast<const uint4*>(p.z + (((size_t)fy[u] * p.H + y) * p.W + x) * p.C + c0));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!act[u]) continue;
+      const int f = fy[u], yi = yy[u], xi = xx[u];
       const int b = p.inv_map ? __ldg(p.inv_map + f) : -1;
-      if (pooled) {
-        float da[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.da + (((size_t)f * Hi + yi) * Wi + xi) * p.da_cpitch + p.da_coff + c0)), da);
-        float zv[4][8], yv[4][8];
+      float da[8];
+      unpack8(dav[u][0], da);
+      if (UPS) {
+        float t1[8], t2[8], t3[8];
+        unpack8(dav[u][1 % ND], t1); unpack8(dav[u][2 % ND], t2); unpack8(dav[u][3 % ND], t3);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int y = 2 * yi + (q >> 1), x = 2 * xi + (q & 1);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(p.z + (((size_t)f * p.H + y) * p.W + x) * p.C + c0)), zv[q]);
+        for (int e = 0; e < 8; ++e) da[e] = (da[e] + t1[e]) + (t2[e] + t3[e]);
+      }
+      float zv[NQ][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+      for (int q = 0; q < NQ; ++q) unpack8(zvv[u][q], zv[q]);
+      int am[8];
+      if (POOLED) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float best = -INFINITY;
+          am[e] = 0;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
             float v = fmaf(zv[q][e], sc[e], sh[e]);
             if (p.lrelu) v = lrelu(v);
-            yv[q][e] = bf16_round(v);  // the forward max-pool compared bf16-rounded activations
+            v = bf16_round(v);  // the forward max-pool compared bf16-rounded activations; first maximum wins
+            if (v > best) { best = v; am[e] = q; }
           }
         }
-        float gq[4][8];
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int y = POOLED ? 2 * yi + (q >> 1) : yi, x = POOLED ? 2 * xi + (q & 1) : xi;
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = POOLED ? (am[e] == q ? da[e] : 0.f) : da[e];
+        if (b >= 0) add_skip8(p, b, y, x, c0, g);
+        float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          int am = 0;
-          float best = yv[0][e];
-#pragma unroll
-          for (int q = 1; q < 4; ++q) if (yv[q][e] > best) { best = yv[q][e]; am = q; }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) gq[q][e] = (q == am) ? da[e] : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int y = 2 * yi + (q >> 1), x = 2 * xi + (q & 1);
-          if (b >= 0) {
-            for (int t = 0; t < p.nt; ++t) {
-              float sk[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(p.skip + ((((size_t)t * p.B + b) * p.H + y) * p.W + x) * p.skip_cpitch + p.skip_coff + c0)), sk);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) gq[q][e] += sk[e];
-            }
-          }
-          float gout[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float pre = fmaf(zv[q][e], sc[e], sh[e]);
-            const float g = gq[q][e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
-            const float gr = bf16_round(g);
-            gout[e] = gr;
-            s1[e] += gr;
-            s2[e] = fmaf(gr, (zv[q][e] - mu[e]) * is[e], s2[e]);
-          }
-          *reinterpret_cast<uint4*>(p.g + (((size_t)f * p.H + y) * p.W + x) * p.C + c0) = pack8(gout);
-        }
-      } else {
-        const int y = yi, x = xi;
-        float zv[8], gsum[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.z + (((size_t)f * p.H + y) * p.W + x) * p.C + c0)), zv);
-        if (p.da_mode == SRVP_SRC_UP2) {
-          const int W2 = p.W * 2;
-          const __nv_bfloat16* base = p.da + (((size_t)f * (p.H * 2) + 2 * y) * W2 + 2 * x) * p.da_cpitch + p.da_coff + c0;
-          float t0[8], t1[8], t2v[8], t3[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base)), t0);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + p.da_cpitch)), t1);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)W2 * p.da_cpitch)), t2v);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)(W2 + 1) * p.da_cpitch)), t3);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) gsum[e] = (t0[e] + t1[e]) + (t2v[e] + t3[e]);
-        } else {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(p.da + (((size_t)f * p.H + y) * p.W + x) * p.da_cpitch + p.da_coff + c0)), gsum);
-        }
-        if (b >= 0) {
-          for (int t = 0; t < p.nt; ++t) {
-            float sk[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.skip + ((((size_t)t * p.B + b) * p.H + y) * p.W + x) * p.skip_cpitch + p.skip_coff + c0)), sk);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) gsum[e] += sk[e];
+          const float pre = fmaf(zv[q][e], sc[e], sh[e]);
+          const float gg = g[e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
+          if (APPLY) {
+            o[e] = fmaf(k0[e], gg, fmaf(zv[q][e], ka[e], kb[e]));
+          } else {
+            s1[e] += gg;
+            s2[e] = fmaf(gg, fmaf(zv[q][e], ka[e], -kb[e]), s2[e]);
           }
         }
-        float gout[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float pre = fmaf(zv[e], sc[e], sh[e]);
-          const float g = gsum[e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
-          const float gr = bf16_round(g);
-          gout[e] = gr;
-          s1[e] += gr;
-          s2[e] = fmaf(gr, (zv[e] - mu[e]) * is[e], s2[e]);
-        }
-        *reinterpret_cast<uint4*>(p.g + (((size_t)f * p.H + y) * p.W + x) * p.C + c0) = pack8(gout);
+        if (APPLY) *reinterpret_cast<uint4*>(p.g + (((size_t)f * p.H + y) * p.W + x) * p.C + c0) = pack8(o);
       }
     }
   }
-  // block reduction over pixel lanes (fixed order -> deterministic)
+  if (!APPLY) {
+    // block reduction over pixel lanes (fixed order -> deterministic)
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { red[tid * 17 + e] = s1[e]; red[tid * 17 + 8 + e] = s2[e]; }
-  __syncthreads();
-  if (tid < cpp) {
-    float a1[8], a2[8];
+    for (int e = 0; e < 8; ++e) { red[tid * 17 + e] = s1[e]; red[tid * 17 + 8 + e] = s2[e]; }
+    __syncthreads();
+    if (tid < cpp) {
+      float a1[8], a2[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      const float* r = red + (l * cpp + tid) * 17;
+      for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        const float* r = red + (l * cpp + tid) * 17;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { a1[e] += r[e]; a2[e] += r[8 + e]; }
-    }
+        for (int e = 0; e < 8; ++e) { a1[e] += r[e]; a2[e] += r[8 + e]; }
+      }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float* dst = p.partial + ((size_t)blockIdx.x * p.C + tid * 8 + e) * 2;
-      dst[0] = a1[e];
-      dst[1] = a2[e];
+      for (int e = 0; e < 8; ++e) {
+        float* dst = p.partial + ((size_t)blockIdx.x * p.C + tid * 8 + e) * 2;
+        dst[0] = a1[e];
+        dst[1] = a2[e];
+      }
     }
   }
 }
 
-// c1 = sum(g)/n, c2 = sum(g*xhat)/n; dgamma += sum(g*xhat), dbeta += sum(g). One warp per channel.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float* __restrict__ c1, float* __restrict__ c2,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+// c1 = sum(g)/n, c2 = sum(g*xhat)/n; dgamma += sum(g*xhat), dbeta += sum(g). Same block shape as bn_finalize_kernel.
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float* __restrict__ c1,
+                                                             float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double r1[8][32], r2[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int r = lane; r < rows; r += 32) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
-    s1 += v.x;
-    s2 += v.y;
+  if (c < C) {
+    for (int r = rl; r < rows; r += 8) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
+      s1 += v.x;
+      s2 += v.y;
+    }
   }
+  r1[rl][cl] = s1;
+  r2[rl][cl] = s2;
+  __syncthreads();
+  if (rl == 0 && c < C) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane == 0) {
+    for (int k = 1; k < 8; ++k) { s1 += r1[k][cl]; s2 += r2[k][cl]; }
     c1[c] = (float)(s1 / count);
     c2[c] = (float)(s2 / count);
     if (dgamma != nullptr) dgamma[c] += (float)s2;
     if (dbeta != nullptr) dbeta[c] += (float)s1;
   }
-}
-
-// dz = gamma*invstd * (g - c1 - xhat*c2), in place on g.
-__global__ void bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ z, const float* __restrict__ gamma,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ c1,
-                                    const float* __restrict__ c2, long long total_chunks, int C) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_chunks) return;
-  const int c0 = (int)(i % (C / 8)) * 8;
-  float gv[8], zv[8], o[8];
-  unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(z + i * 8)), zv);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float is = __ldg(invstd + c0 + e);
-    const float xh = (zv[e] - __ldg(mean + c0 + e)) * is;
-    o[e] = __ldg(gamma + c0 + e) * is * (gv[e] - __ldg(c1 + c0 + e) - xh * __ldg(c2 + c0 + e));
-  }
-  *reinterpret_cast<uint4*>(g + i * 8) = pack8(o);
 }
 
 // dz16[f,y,x,c] = dxhat[f,c,y,x] * xhat * (1 - xhat) for c < C, zero padding up to 16 channels.
@@ -480,7 +490,7 @@ extern "C" int srvp_bn_finalize(const float* partial, int32_t rows, int32_t C, d
                                 float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* invstd,
                                 void* stream) {
   SRVP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must both be given or both be NULL");
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale,
                                                                     shift, mean, invstd);
   return check_launch("bn_finalize");
 }
@@ -501,8 +511,8 @@ extern "C" int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, f
 }
 
 static int bn_bwd_blocks(long long items) {
-  long long nb = (items + 2047) / 2048;
-  if (nb > 4096) nb = 4096;
+  long long nb = (items + 1023) / 1024;
+  if (nb > 8192) nb = 8192;
   if (nb < 1) nb = 1;
   return (int)nb;
 }
@@ -512,9 +522,10 @@ extern "C" int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int
   return bn_bwd_blocks(items);
 }
 
-extern "C" int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* a, void* stream) {
-  SRVP_REQUIRE(a != nullptr && a->z && a->da && a->g && a->partial, "bn_bwd_reduce: null argument");
-  SRVP_REQUIRE(a->C % 8 == 0 && a->C <= 2048 && 256 % (a->C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", a->C);
+static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gamma, const float* c1, const float* c2, void* stream) {
+  SRVP_REQUIRE(a != nullptr && a->z && a->da, "bn_bwd: null argument");
+  SRVP_REQUIRE(a->C % 8 == 0 && a->C <= 2048 && 256 % (a->C / 8) == 0, "bn_bwd: unsupported channel count %d", a->C);
+  SRVP_REQUIRE(apply ? (a->g != nullptr && gamma && c1 && c2) : (a->partial != nullptr), "bn_bwd: missing output");
   BnBwdDev d{};
   d.z = reinterpret_cast<const __nv_bfloat16*>(a->z);
   d.scale = a->scale; d.shift = a->shift; d.mean = a->mean; d.invstd = a->invstd;
@@ -527,27 +538,31 @@ extern "C" int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* a, void* stream) {
   d.partial = a->partial;
   d.F = a->frames; d.H = a->H; d.W = a->W; d.C = a->C; d.lrelu = a->lrelu;
   const bool pooled = a->da_mode == SRVP_SRC_POOL2;
-  if (pooled) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "bn_bwd_reduce: pooled mode needs even size");
+  if (pooled || a->da_mode == SRVP_SRC_UP2) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0 || !pooled, "bn_bwd: pooled mode needs even size");
   const long long items = pooled ? (long long)a->frames * (a->H / 2) * (a->W / 2) : (long long)a->frames * a->H * a->W;
   const int nb = bn_bwd_blocks(items);
   const int ipb = (int)((items + nb - 1) / nb);
-  bn_bwd_reduce_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(d, items, ipb);
-  return check_launch("bn_bwd_reduce");
+  cudaStream_t st = (cudaStream_t)stream;
+#define SRVP_BN_LAUNCH(MODE)                                                                    \
+  if (apply) bn_bwd_kernel<MODE, true><<<nb, 256, 0, st>>>(d, items, ipb, gamma, c1, c2);       \
+  else bn_bwd_kernel<MODE, false><<<nb, 256, 0, st>>>(d, items, ipb, nullptr, nullptr, nullptr);
+  if (a->da_mode == SRVP_SRC_POOL2) { SRVP_BN_LAUNCH(SRVP_SRC_POOL2) }
+  else if (a->da_mode == SRVP_SRC_UP2) { SRVP_BN_LAUNCH(SRVP_SRC_UP2) }
+  else { SRVP_BN_LAUNCH(SRVP_SRC_DIRECT) }
+#undef SRVP_BN_LAUNCH
+  return check_launch(apply ? "bn_bwd_apply" : "bn_bwd_reduce");
 }
+
+extern "C" int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* a, void* stream) { return bn_bwd_launch(a, false, nullptr, nullptr, nullptr, stream); }
 
 extern "C" int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,
                                     void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, count, c1, c2, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, count, c1, c2, dgamma, dbeta);
   return check_launch("bn_bwd_finalize");
 }
 
-extern "C" int srvp_bn_bwd_apply(srvp_bf16* g, const srvp_bf16* z, const float* gamma, const float* mean, const float* invstd, const float* c1,
-                                 const float* c2, int64_t positions, int32_t C, void* stream) {
-  SRVP_REQUIRE(C % 8 == 0, "bn_bwd_apply: C must be a multiple of 8");
-  const long long total = positions * (C / 8);
-  bn_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z),
-                                                                                gamma, mean, invstd, c1, c2, total, C);
-  return check_launch("bn_bwd_apply");
+extern "C" int srvp_bn_bwd_apply(const srvp_bn_bwd_args* a, const float* gamma, const float* c1, const float* c2, void* stream) {
+  return bn_bwd_launch(a, true, gamma, c1, c2, stream);
 }
 
 extern "C" int srvp_sigmoid_bwd_nchw_to_nhwc16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,

@@ -301,10 +301,9 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     count = float(frames * H * W)
     check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(c12[0]), ptr(c12[1]),
                                     ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
-    check(lib().srvp_bn_bwd_apply(ptr(g), ptr(z), ptr(gamma), ptr(state.mean), ptr(state.invstd), ptr(c12[0]), ptr(c12[1]),
-                                 c_i64(frames * H * W), c_int(C), stream_ptr()), 'bn_bwd_apply')
+    check(lib().srvp_bn_bwd_apply(ctypes.byref(a), ptr(gamma), ptr(c12[0]), ptr(c12[1]), stream_ptr()), 'bn_bwd_apply')
     n = float(frames * H * W * C)
-    _account(0.0, 2.0 * n * (2 + 3) + 2.0 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0))
+    _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0))
     return g
 
 
