@@ -186,6 +186,66 @@ typedef struct {
 } srvp_gemm_args;
 int srvp_gemm(const srvp_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Latent residual dynamics: the Euler loop of generate() (module/srvp.py:325-413, _residual_step :300-323) as ONE
+ * persistent launch. p_z = MLP(ny -> nh ... -> 2nz), dynamics = MLP(ny+nz -> nh ... -> ny) (module/mlp.py:47-90):
+ *   every Euler step s (os sub-steps per frame): first sub-step of frame f: p_z(y) -> pz_out[f]; z[f] = z_post[f] for
+ *   f < n_post (posterior sample, srvp.py:387) else mu + (softplus(rho)+1e-8)*eps[f] from p_z (prior, srvp.py:392);
+ *   res = dt * dynamics(cat[y, z[f]]); y += res (srvp.py:320-322).
+ * Weights are packed by srvp_pack_linear (bf16 128x64 tiles); accumulation, bias, state and outputs are fp32.
+ * ---------------------------------------------------------------------------------------------- */
+enum { SRVP_MAX_MLP_LAYERS = 6 };
+typedef struct {
+  int32_t nlayers;
+  int32_t din[SRVP_MAX_MLP_LAYERS], dout[SRVP_MAX_MLP_LAYERS];
+  const srvp_bf16* wpack[SRVP_MAX_MLP_LAYERS]; /* srvp_pack_linear of weight (dout, din) [forward] or of its transpose [backward] */
+  const float* bias[SRVP_MAX_MLP_LAYERS];
+} srvp_mlp_desc;
+int64_t srvp_pack_linear_size(int32_t dout, int32_t din); /* elements of the packed buffer */
+/* element (o, k) of the packed operand = w[o*stride_o + k*stride_k]; nn.Linear weight (dout, din): (din, 1); its transpose: (1, din) */
+int srvp_pack_linear(const float* w, srvp_bf16* out, int32_t dout, int32_t din, int64_t stride_o, int64_t stride_k, void* stream);
+
+typedef struct {
+  srvp_mlp_desc p_z, dynamics;
+  const float* y0;      /* (B, ny) */
+  const float* z_post;  /* (n_post, B, nz) */
+  const float* eps;     /* (nt-1, B, nz); only read for frames >= n_post */
+  float* y_all;         /* out (os*(nt-1)+1, B, ny): every Euler state, row 0 = y0 */
+  float* pz_out;        /* out (nt-1, B, 2nz) */
+  float* z_out;         /* out (nt-1, B, nz) */
+  float* res_out;       /* out (os*(nt-1), B, ny) */
+  srvp_bf16* hid_p;     /* out (nlayers-1, nt-1, B, nh): post-ReLU hidden activations, saved for the backward pass */
+  srvp_bf16* hid_d;     /* out (nlayers-1, os*(nt-1), B, nh) */
+  int32_t B, ny, nz, nh, nt, os, n_post;
+  float dt;
+} srvp_latent_fwd_args;
+int srvp_latent_fwd(const srvp_latent_fwd_args* args, void* stream);
+
+/* Reverse-time backward of the same loop (autograd of srvp.py:377-405 via train.py:119). The MLP descriptors hold the
+ * TRANSPOSED weights (srvp_pack_linear with strides (1, din)) with the layers in backward order, dims = (dout, din) swapped.
+ * g_y: gradient w.r.t. every Euler state (zero rows where a state is not consumed downstream); g_res, g_pz: gradients of
+ * the residuals (L2 term, train.py:103) and of the prior parameters (KL, train.py:97-98).
+ * Besides d_y0 and d_z, the pre-activation gradients of all hidden layers / steps are saved so that the weight gradients
+ * are plain GEMMs over K = steps*B (srvp_gemm) and the bias gradients column sums (srvp_colsum). */
+typedef struct {
+  srvp_mlp_desc p_z_t, dynamics_t;
+  const srvp_bf16* hid_p; /* as written by srvp_latent_fwd */
+  const srvp_bf16* hid_d;
+  const float* g_y;     /* (os*(nt-1)+1, B, ny) */
+  const float* g_res;   /* (os*(nt-1), B, ny) */
+  const float* g_pz;    /* (nt-1, B, 2nz) */
+  float* d_y0;          /* out (B, ny) */
+  float* d_z;           /* out (nt-1, B, nz) */
+  float* dout_d;        /* out (os*(nt-1), B, ny): gradient w.r.t. the dynamics MLP output */
+  srvp_bf16* dpre_p;    /* out (nlayers-1, nt-1, B, nh) */
+  srvp_bf16* dpre_d;    /* out (nlayers-1, os*(nt-1), B, nh) */
+  int32_t B, ny, nz, nh, nt, os;
+  float dt;
+} srvp_latent_bwd_args;
+int srvp_latent_bwd(const srvp_latent_bwd_args* args, void* stream);
+/* out[c] += sum over rows of in[r*ld + c] (bias gradients); dtype SRVP_F32 or SRVP_BF16. */
+int srvp_colsum(const void* in, int32_t dtype, int64_t rows, int32_t cols, int64_t ld, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,27 @@ class GemmArgs(ctypes.Structure):
                 ('accumulate', c_int), ('split_k', c_int)]
 
 
+MAX_MLP_LAYERS = 6
+
+
+class MlpDesc(ctypes.Structure):
+    _fields_ = [('nlayers', c_int), ('din', c_int * MAX_MLP_LAYERS), ('dout', c_int * MAX_MLP_LAYERS),
+                ('wpack', c_ptr * MAX_MLP_LAYERS), ('bias', c_ptr * MAX_MLP_LAYERS)]
+
+
+class LatentFwdArgs(ctypes.Structure):
+    _fields_ = [('p_z', MlpDesc), ('dynamics', MlpDesc), ('y0', c_ptr), ('z_post', c_ptr), ('eps', c_ptr), ('y_all', c_ptr),
+                ('pz_out', c_ptr), ('z_out', c_ptr), ('res_out', c_ptr), ('hid_p', c_ptr), ('hid_d', c_ptr), ('B', c_int),
+                ('ny', c_int), ('nz', c_int), ('nh', c_int), ('nt', c_int), ('os', c_int), ('n_post', c_int),
+                ('dt', ctypes.c_float)]
+
+
+class LatentBwdArgs(ctypes.Structure):
+    _fields_ = [('p_z_t', MlpDesc), ('dynamics_t', MlpDesc), ('hid_p', c_ptr), ('hid_d', c_ptr), ('g_y', c_ptr), ('g_res', c_ptr),
+                ('g_pz', c_ptr), ('d_y0', c_ptr), ('d_z', c_ptr), ('dout_d', c_ptr), ('dpre_p', c_ptr), ('dpre_d', c_ptr),
+                ('B', c_int), ('ny', c_int), ('nz', c_int), ('nh', c_int), ('nt', c_int), ('os', c_int), ('dt', ctypes.c_float)]
+
+
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 SRC_DIRECT, SRC_POOL2, SRC_UP2 = 0, 1, 2
@@ -66,6 +87,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.srvp_last_error.restype = ctypes.c_char_p
         _lib.srvp_launch_count.restype = ctypes.c_uint64
+        _lib.srvp_pack_linear_size.restype = ctypes.c_int64
         for name in EXPORTS:
             getattr(_lib, name)  # AttributeError if the header and the library disagree
     return _lib
@@ -78,6 +100,7 @@ EXPORTS = [
     'srvp_materialize_src', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd',
+    'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum',
 ]
 
 

@@ -135,36 +135,30 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         return y_t + res_tp1, res_tp1
 
     def generate(self, y_0, hx, nt, dt, remove_intermediate=True):
-        """module/srvp.py:325-413"""
-        y, z, q_z_params, p_z_params, res = [y_0], [], [], [], []
-        hx_z = self.inf_z(hx)[0] if len(hx) > 0 else []
+        """module/srvp.py:325-413. The whole Euler loop is one persistent kernel launch (srvp_b200/csrc/latent.cu)."""
+        from .. import latent
         assert (1 / dt).is_integer()
         oversampling = int(1 / dt)
-        y_tm1, t_data = y_0, 0
-        for t in np.linspace(dt, nt - 1, oversampling * (nt - 1)):
-            prev_t_data, t_data = t_data, int(math.ceil(t))
-            if t_data != prev_t_data:
-                p_z_t_params = self.p_z(y_tm1)
-                p_z_params.append(p_z_t_params)
-                if t_data < len(hx):
-                    z_t, q_z_t_params = self.infer_z(hx_z[t_data])
-                    q_z_params.append(q_z_t_params)
-                else:
-                    assert not self.training
-                    z_t = self._rsample(p_z_t_params)
-                z.append(z_t)
-            else:
-                z_t = z[-1]
-            y_t, res_t = self._residual_step(y_tm1, z_t, dt)
-            y_tm1 = y_t
-            if not remove_intermediate or t.is_integer():
-                y.append(y_t)
-            res.append(res_t)
-        y = torch.stack(y)
-        z = torch.stack(z) if len(z) > 0 else None
-        q_z_params = torch.stack(q_z_params) if len(q_z_params) > 0 else None
-        p_z_params = torch.stack(p_z_params) if len(p_z_params) > 0 else None
-        return y, z, q_z_params, p_z_params, torch.stack(res)
+        bsz = y_0.shape[0]
+        n_obs = len(hx)
+        n_post = max(0, min(nt, n_obs) - 1)          # frames 1..n_post have an observation: z ~ q(z | x)  (srvp.py:385-388)
+        if n_post < nt - 1:
+            assert not self.training                 # srvp.py:391
+        q_z_params, z_post = None, None
+        if n_obs > 0:
+            hx_z = self.inf_z(hx)[0]
+        # noise in the reference's order: one (B, nz) draw per generated frame (posterior or prior alike)
+        eps = torch.stack([self._normal((bsz, self.nz), y_0) for _ in range(nt - 1)]) if nt > 1 else None
+        if n_post > 0:
+            q_z_params = self.q_z(hx_z[1:n_post + 1])
+            loc, raw_scale = torch.chunk(q_z_params, 2, -1)
+            z_post = loc + eps[:n_post] * (nn.functional.softplus(raw_scale) + 1e-8)
+        y_all, p_z_params, z, res = latent.latent_loop(self.p_z, self.dynamics, y_0, z_post, eps, nt, oversampling, float(dt), n_post,
+                                                        self.nh_res)
+        y = y_all[::oversampling] if remove_intermediate else y_all
+        if n_post == nt - 1 and z_post is not None:
+            z = z_post                              # keep the differentiable posterior samples in the returned tuple
+        return y, (z if nt > 1 else None), q_z_params, (p_z_params if nt > 1 else None), res
 
     def forward(self, x, nt, dt, remove_intermediate=True):
         """module/srvp.py:415-470: returns (x_, y, z, w, q_y_0_params, q_z_params, p_z_params, res)."""
