@@ -1,0 +1,118 @@
+"""CPU suite, part 2: host logic, the C-ABI exports, and the multi-rank plumbing on gloo (no kernel is launched here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from common import ROOT, ARG_ORDER, build_model
+
+
+def test_library_exports_every_declared_symbol():
+    from srvp_b200 import _lib
+    lib = _lib.lib()
+    hdr = open(os.path.join(ROOT, 'include', 'srvp_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(srvp_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in include/srvp_b200.h but not exported'
+    assert set(_lib.EXPORTS) == declared
+    assert lib.srvp_version() == 100
+    assert isinstance(lib.srvp_last_error(), bytes)
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors must have the C layout (checked against a tiny C program compiled with gcc)."""
+    from srvp_b200 import _lib
+    src = '#include <stdio.h>\n#include "srvp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(srvp_conv_src), ' \
+          'sizeof(srvp_conv3x3_args), sizeof(srvp_wgrad3x3_args), sizeof(srvp_bn_bwd_args), sizeof(srvp_gemm_args), ' \
+          'sizeof(srvp_latent_fwd_args), sizeof(srvp_latent_bwd_args));return 0;}\n'
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, 't.c'), 'w').write(src)
+        subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')], check=True)
+        sizes = [int(v) for v in subprocess.run([os.path.join(d, 't')], capture_output=True, text=True, check=True).stdout.split()]
+    mirrors = [_lib.ConvSrc, _lib.Conv3x3Args, _lib.Wgrad3x3Args, _lib.BnBwdArgs, _lib.GemmArgs, _lib.LatentFwdArgs, _lib.LatentBwdArgs]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_no_cpu_fallback():
+    """The product path refuses to run without CUDA instead of silently falling back."""
+    cfg = dict(nx=64, nc=1, nf=64, nhx=128, ny=20, nz=20, skipco=True, nt_inf=2, nh_inf=256, nlayers_inf=3, nh_res=512, nlayers_res=4,
+               archi='vgg')
+    m = build_model(cfg, 1.41, 0)
+    with pytest.raises(RuntimeError):
+        m.encoder(torch.rand(2, 1, 64, 64))
+
+
+def test_class_surface_matches_reference_contract():
+    """Attributes, sub-module names and method names used by train.py / test.py."""
+    cfg = dict(nx=64, nc=3, nf=64, nhx=128, ny=50, nz=50, skipco=True, nt_inf=2, nh_inf=256, nlayers_inf=3, nh_res=512, nlayers_res=4,
+               archi='vgg')
+    m = build_model(cfg, 1.41, 0)
+    for a in ['nx', 'nc', 'ny', 'nz', 'skipco', 'nt_inf', 'nh_inf', 'nlayers_inf', 'nh_res', 'nlayers_res', 'nhx']:
+        assert getattr(m, a) == cfg[a]
+    assert [n for n, _ in m.named_children()] == ['encoder', 'decoder', 'w_proj', 'w_inf', 'q_y', 'inf_z', 'q_z', 'p_z', 'dynamics']
+    for meth in ['init', 'encode', 'decode', 'infer_w', 'infer_y', 'infer_z', '_residual_step', 'generate', 'forward']:
+        assert callable(getattr(m, meth))
+    assert sum(p.numel() for p in m.parameters()) == 23847390          # SURVEY.md App. E (VGG nc=3)
+    assert len(m.state_dict()) == 159
+    with pytest.raises(ValueError):
+        from srvp_b200.module import conv
+        conv.encoder_factory('resnet', 64, 3, 128, 64)
+    sbn = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m)               # train.py:283 walks the BatchNorm2d children
+    assert any(isinstance(x, torch.nn.SyncBatchNorm) for x in sbn.modules())
+
+
+def test_rng_consumption_order_matches_reference():
+    """Host draws (skip frame, infer_w frames, noise) come from torch's CPU generator in the reference's order (App. D)."""
+    from oracle import srvp_oracle as O
+    cfg = dict(skipco=True, nt_inf=2, ny=5, nz=7)
+    torch.manual_seed(3)
+    r = O.draw_randoms(cfg, 6, 6, 4, training=True)
+    torch.manual_seed(3)
+    t_skip = torch.randint(6, size=(4,))
+    t_w = torch.stack([torch.randperm(6)[:2] for _ in range(4)], 1)
+    e_y = torch.empty(4, 5).normal_()
+    e_z = [torch.empty(4, 7).normal_() for _ in range(5)]
+    assert torch.equal(r['t_skip'], t_skip) and torch.equal(r['t_w'], t_w) and torch.equal(r['eps_y'], e_y)
+    assert all(torch.equal(a, b) for a, b in zip(r['eps_z'], e_z))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from srvp_b200 import parallel
+    # batch sharding: every rank gets a contiguous slice of the videos; together they cover the global batch exactly once
+    lo, hi = parallel.shard_bounds(10, rank, world)
+    # gradient averaging over one flat bucket
+    g = [torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))]
+    parallel.allreduce_mean_(g)
+    # batch-norm statistic exchange: (sum, sumsq, count) partials are summed over ranks
+    part = torch.tensor([[[1.0 + rank, 2.0 + rank]]])
+    tot, cnt = parallel.allreduce_bn_partial(part, 5.0 + rank)
+    q.put((rank, lo, hi, g[0].tolist(), g[1].flatten().tolist(), tot.flatten().tolist(), cnt))
+    dist.destroy_process_group()
+
+
+def test_two_rank_plumbing_on_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 5, 5, 10)
+    for r in res:
+        assert r[3] == [1.5] * 3 and r[4] == [15.0] * 4
+        assert r[5] == [3.0, 5.0] and r[6] == 11.0
