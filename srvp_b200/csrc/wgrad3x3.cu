@@ -23,11 +23,11 @@ namespace srvp {
 
 namespace {
 
-constexpr int kWgThreads = 704;  // warps 0-3 epilogue, 4-19 asynchronous-copy issuers, 20-21 MMA issuers
-constexpr int kCopyThreads = 512;
+constexpr int kWgThreads = 320;  // warps 0-3 epilogue, 4-7 asynchronous-copy issuers, 8-9 MMA issuers
+constexpr int kCopyThreads = 128;
 constexpr int PT = 128;          // pixels (GEMM-K) per pipeline stage
 constexpr int kMaxStages = 4;
-constexpr int kSlots = 3;        // copy items per thread and operand (halo tile on the M side: up to 3)
+constexpr int kSlots = 3;        // halo-tile rows per copy thread (PH <= 3 * 128)
 
 struct PlainDev {
   const __nv_bfloat16* ptr;
@@ -51,16 +51,15 @@ struct WgradDev {
   int dbg;           // development only: 1 = skip loads, 2 = skip MMAs
 };
 
-// One copy item = 4 (or CH) consecutive 16-byte chunks of one pixel row of a tile. A thread keeps the (frame, y, x)
-// position of its items and advances it by PT virtual pixels per pipeline step: no divisions in the steady state.
+// A copy thread owns whole pixel rows of the two operand tiles (one row of the plain tile, up to three of the halo tile). It keeps
+// the (frame, y, x) position of each row and advances it by PT virtual pixels per pipeline step: no divisions in the steady state.
 struct RowPos {
-  int f, y, x;      // y may be -1.. for rows before the first frame (f < 0 marks "before the tensor")
-  int row, grp;     // tile row and chunk group of this item; row < 0: slot unused
+  int f, y, x;      // f < 0 marks "before the tensor" (first halo rows of the very first step)
 };
 
 __device__ __forceinline__ void rowpos_init(RowPos& rp, long long v, int HpWp, int Wp) {
-  if (v < 0) {  // only the first halo rows of the very first step: mark invalid but keep advancing consistently
-    const long long vv = v + (long long)HpWp;  // shift by one virtual frame
+  if (v < 0) {
+    const long long vv = v + (long long)HpWp;  // shift by one virtual frame, keep advancing consistently
     rp.f = -1;
     rp.y = (int)(vv / Wp);
     rp.x = (int)(vv - (long long)rp.y * Wp);
@@ -83,17 +82,16 @@ __device__ __forceinline__ void rowpos_advance(RowPos& rp, int df, int dy, int d
   rp.f += df + cy;
 }
 
-template <int G>
-__device__ __forceinline__ void copy_item(const PlainDev& t, const WgradDev& p, uint8_t* tile, int rows, const RowPos& rp, int c0) {
+// Asynchronous 16-byte copies (cp.async, zero-filled for pad pixels) of `nch` channel chunks of one pixel row into tile row `row`.
+__device__ __forceinline__ void copy_row(const PlainDev& t, const WgradDev& p, uint8_t* tile, int rows, int row, const RowPos& rp, int c0, int nch) {
   const bool valid = (rp.f >= 0) && (rp.f < p.F) && (rp.y < p.H) && (rp.x < p.W);
-  const int cfirst = c0 + rp.grp * G * 8;
-  const __nv_bfloat16* base = valid ? t.ptr + (((size_t)rp.f * p.H + rp.y) * p.W + rp.x) * t.cpitch + t.coff + cfirst : t.ptr;
-  uint8_t* dst = tile + ((size_t)(rp.grp * G) * rows + rp.row) * 16;
-#pragma unroll
-  for (int j = 0; j < G; ++j) {
-    const bool ok = valid && (cfirst + j * 8 < t.channels);
-    cp_async16(dst + (size_t)j * rows * 16, ok ? base + j * 8 : t.ptr, ok ? 16u : 0u);
-  }
+  const __nv_bfloat16* src = valid ? t.ptr + (((size_t)rp.f * p.H + rp.y) * p.W + rp.x) * t.cpitch + t.coff + c0 : t.ptr;
+  const uint32_t nbytes = valid ? 16u : 0u;
+  const int step = valid ? 8 : 0;
+  uint8_t* dst = tile + (size_t)row * 16;
+  const size_t dstep = (size_t)rows * 16;
+#pragma unroll 4
+  for (int j = 0; j < nch; ++j) cp_async16(dst + j * dstep, src + j * step, nbytes);
 }
 
 template <int NBc>
@@ -123,6 +121,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  // chunk planes of channels that do not exist (operands narrower than the tile) are never written by the copy warps: zero once
+  for (size_t i = tid; i < kStages * stage_bytes / 16; i += kWgThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -138,54 +139,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
   const int nsteps = max(0, step1 - step0);
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp >= 4 && warp < 20) {
+  if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ asynchronous copies (cp.async, zero-fill for pads)
     const int lt = tid - 128;
     const PlainDev& mop = p.halo_on_m ? p.act : p.dz;
     const PlainDev& nop = p.halo_on_m ? p.dz : p.act;
     const int m_c0 = mblk * 128, n_c0 = nblk * NBc;
-    const long long vm = (long long)step0 * PT - (p.halo_on_m ? p.Wp + 1 : 0);
-    const long long vn = (long long)step0 * PT - (p.halo_on_m ? 0 : p.Wp + 1);
-    RowPos ms[kSlots], ns;
-    const int m_items = m_rows * (MCH / GM), n_items = n_rows * (NCH / GN);
+    // chunks that actually exist in the tensors; the remaining chunk planes of the tiles stay zero (cleared once below)
+    const int m_nch = min(MCH, max(0, (mop.channels - m_c0 + 7) / 8)), n_nch = min(NCH, max(0, (nop.channels - n_c0 + 7) / 8));
+    const PlainDev& hop = p.halo_on_m ? mop : nop;   // operand staged with the halo (PH rows), the other one has PT rows
+    const PlainDev& pop = p.halo_on_m ? nop : mop;
+    const int h_c0 = p.halo_on_m ? m_c0 : n_c0, p_c0 = p.halo_on_m ? n_c0 : m_c0;
+    const int h_nch = p.halo_on_m ? m_nch : n_nch, p_nch = p.halo_on_m ? n_nch : m_nch;
+    const size_t h_off = p.halo_on_m ? 0 : m_bytes, p_off = p.halo_on_m ? m_bytes : 0;
+    RowPos pr, hr[kSlots];
+    rowpos_init(pr, (long long)step0 * PT + lt, HpWp, p.Wp);
 #pragma unroll
-    for (int k = 0; k < kSlots; ++k) {
-      const int it = lt + k * kCopyThreads;
-      ms[k].row = -1;
-      if (it < m_items) {
-        ms[k].grp = it / m_rows;
-        ms[k].row = it - ms[k].grp * m_rows;
-        rowpos_init(ms[k], vm + ms[k].row, HpWp, p.Wp);
-      }
-    }
-    ns.row = -1;
-    if (lt < n_items) {
-      ns.grp = lt / n_rows;
-      ns.row = lt - ns.grp * n_rows;
-      rowpos_init(ns, vn + ns.row, HpWp, p.Wp);
-    }
+    for (int k = 0; k < kSlots; ++k) rowpos_init(hr[k], (long long)step0 * PT - p.Wp - 1 + lt + k * kCopyThreads, HpWp, p.Wp);
     const int df = PT / HpWp, dy = (PT % HpWp) / p.Wp, dx = (PT % HpWp) % p.Wp;
     for (int i = 0; i < nsteps; ++i) {
       const int st = i % kStages;
       mbar_wait(&empty[st], ((i / kStages) & 1) ^ 1);
-      uint8_t* mt = smem + st * stage_bytes;
-      uint8_t* nt = mt + m_bytes;
+      uint8_t* base = smem + st * stage_bytes;
       if ((p.dbg & 3) != 1) {
+        copy_row(pop, p, base + p_off, PT, lt, pr, p_c0, p_nch);
 #pragma unroll
         for (int k = 0; k < kSlots; ++k)
-          if (ms[k].row >= 0) copy_item<GM>(mop, p, mt, m_rows, ms[k], m_c0);
-        if (ns.row >= 0) copy_item<GN>(nop, p, nt, n_rows, ns, n_c0);
+          if (lt + k * kCopyThreads < PH) copy_row(hop, p, base + h_off, PH, lt + k * kCopyThreads, hr[k], h_c0, h_nch);
       }
       cp_async_arrive_noinc(&full[st]);
+      rowpos_advance(pr, df, dy, dx, p.Hp, p.Wp);
 #pragma unroll
-      for (int k = 0; k < kSlots; ++k) rowpos_advance(ms[k], df, dy, dx, p.Hp, p.Wp);
-      rowpos_advance(ns, df, dy, dx, p.Hp, p.Wp);
+      for (int k = 0; k < kSlots; ++k) rowpos_advance(hr[k], df, dy, dx, p.Hp, p.Wp);
     }
-  } else if (warp >= 20) {
-    // ------------------------------------------------------------------ MMA issuers: warp 20 -> taps 0-4, warp 21 -> taps 5-8
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ MMA issuers: warp 8 -> taps 0-4, warp 9 -> taps 5-8
     // (one thread sustains ~1 MMA / 50 cycles, the tensor core accepts one small-N MMA per 40: two issuers close the gap)
     if (lane == 0 && nsteps > 0) {
-      const int tap_lo = warp == 20 ? 0 : 5, tap_hi = warp == 20 ? 5 : 9;
+      const int tap_lo = warp == 8 ? 0 : 5, tap_hi = warp == 8 ? 5 : 9;
       constexpr uint32_t idesc = umma_idesc_bf16(128, NBc, 1, 1);
       const uint32_t base = smem_u32(smem);
       for (int i = 0; i < nsteps; ++i) {
@@ -285,8 +276,7 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   if (splits > d.steps_total) splits = d.steps_total;
   d.splits = splits;
   const size_t m_rows = d.halo_on_m ? d.PH : PT, n_rows = d.halo_on_m ? PT : d.PH;
-  SRVP_REQUIRE((int)(m_rows * 4) <= kSlots * kCopyThreads, "wgrad3x3: M tile has too many copy items (W=%d)", a->W);
-  SRVP_REQUIRE((int)(n_rows * ((NBc / 8) < 4 ? 1 : (NBc / 8) / 4)) <= kCopyThreads, "wgrad3x3: N tile has too many copy items (W=%d)", a->W);
+  SRVP_REQUIRE(d.PH <= kSlots * kCopyThreads, "wgrad3x3: halo tile has too many rows (W=%d)", a->W);
   const size_t stage_bytes = (size_t)16 * m_rows * 16 + (size_t)(NBc / 8) * n_rows * 16;
   int nstg = (int)((227 * 1024 - 256) / stage_bytes);
   if (nstg > kMaxStages) nstg = kMaxStages;
