@@ -105,6 +105,9 @@ def run_ours(args):
     torch.manual_seed(1)
     model = StochasticLatentResidualVideoPredictor(*[CFG[k] for k in ARG_ORDER])
     model.init(res_gain=1.41)
+    if world > 1:
+        # reference multi-GPU semantics (train.py:283): batch-norm statistics over the GLOBAL batch
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     model = model.to(dev).train()
     model.noise_device = 'cuda'
     params = [p for p in model.parameters()]
@@ -186,6 +189,9 @@ def run_ours(args):
     breakdown = {k: dict(ms_per_step=round(v['ms'] / 2, 3), launches=v['launches'] // 2,
                          tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['flops'] else None,
                          gbs=round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1) if v['bytes'] else None) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     frames = SEQ_LEN * BATCH * world
@@ -193,7 +199,7 @@ def run_ours(args):
                 n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
                 config=dict(workload='BAIR VGG64 skipco nc=3 64x64 seq_len=12 batch=192/GPU ny=nz=50 nt_inf=2 n_euler_steps=2; fwd+ELBO+bwd+Adam',
-                            global_batch=BATCH * world, seq_len=SEQ_LEN, parallelism=f'dp{world}',
+                            global_batch=BATCH * world, seq_len=SEQ_LEN, parallelism=f'dp{world}' + (' + SyncBN statistics' if world > 1 else ''),
                             l2='inputs larger than L2: 113 MB batch, >10 GB of activations per step'),
                 e2e=dict(value=round(frames * args.steps / (ms_e2e * 1e-3), 1), unit='frames/s', h2d_bytes_per_step=host[0].numel() * 4,
                          d2h_bytes_per_step=4),

@@ -162,6 +162,13 @@ int srvp_bn_tanh_rows_fwd(const float* z, int32_t rows, int32_t C, const float* 
                           float* out, void* stream);
 int srvp_bn_tanh_rows_bwd(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* gamma, const float* mean,
                           const float* invstd, float* dz, float* dgamma, float* dbeta, void* stream);
+/* The same two steps decomposed for synchronised batch-norm (train.py:283): the (1, C, 2) partial sums are all-reduced over the
+ * ranks between the passes; srvp_bn_finalize / srvp_bn_bwd_finalize consume the totals. */
+int srvp_rows_stats_f32(const float* z, int32_t rows, int32_t C, float* partial, void* stream);
+int srvp_bn_tanh_rows_bwd_reduce(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* mean,
+                                 const float* invstd, float* partial, void* stream);
+int srvp_bn_tanh_rows_bwd_apply(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* gamma,
+                                const float* mean, const float* invstd, const float* c1, const float* c2, float* dz, void* stream);
 /* Backward of torch.sigmoid on the decoder output (conv.py:273-274): dz(frames,H,W,16) = dxhat * xhat * (1 - xhat), NCHW fp32 in. */
 int srvp_sigmoid_bwd_nchw_to_nhwc16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,
                                     void* stream);

@@ -99,7 +99,8 @@ EXPORTS = [
     'srvp_pack_conv3x3_weights', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16', 'srvp_nhwc_bf16_to_nchw_f32',
     'srvp_materialize_src', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
-    'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd',
+    'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
+    'srvp_bn_tanh_rows_bwd_apply',
     'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum',
 ]
 

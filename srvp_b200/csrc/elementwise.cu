@@ -456,6 +456,61 @@ __global__ void __launch_bounds__(256) bn_tanh_rows_bwd_kernel(const float* __re
   }
 }
 
+// Decomposed variants of the two kernels above for synchronised batch-norm (statistics summed over ranks between the passes).
+__global__ void __launch_bounds__(256) rows_stats_f32_kernel(const float* __restrict__ z, int rows, int C, float* __restrict__ partial) {
+  __shared__ double r1[256], r2[256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = tid; r < rows; r += 256) {
+    const double v = z[(size_t)r * C + c];
+    s1 += v;
+    s2 += v * v;
+  }
+  r1[tid] = s1; r2[tid] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { r1[tid] += r1[tid + o]; r2[tid] += r2[tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) { partial[c * 2] = (float)r1[0]; partial[c * 2 + 1] = (float)r2[0]; }
+}
+
+__global__ void __launch_bounds__(256) bn_tanh_rows_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                                        const float* __restrict__ z, int rows, int C, const float* __restrict__ mean,
+                                                                        const float* __restrict__ invstd, float* __restrict__ partial) {
+  __shared__ double r1[256], r2[256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const float mu = mean[c], is = invstd[c];
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = tid; r < rows; r += 256) {
+    const float o = out[(size_t)r * C + c];
+    const float g = dout[(size_t)r * C + c] * (1.f - o * o);
+    s1 += g;
+    s2 += (double)g * ((z[(size_t)r * C + c] - mu) * is);
+  }
+  r1[tid] = s1; r2[tid] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { r1[tid] += r1[tid + o]; r2[tid] += r2[tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) { partial[c * 2] = (float)r1[0]; partial[c * 2 + 1] = (float)r2[0]; }
+}
+
+__global__ void __launch_bounds__(256) bn_tanh_rows_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ z,
+                                                                       long long total, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                       const float* __restrict__ invstd, const float* __restrict__ c1,
+                                                                       const float* __restrict__ c2, float* __restrict__ dz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const float o = out[i];
+  const float g = dout[i] * (1.f - o * o);
+  const float is = invstd[c];
+  const float xh = (z[i] - mean[c]) * is;
+  dz[i] = gamma[c] * is * (g - c1[c] - xh * c2[c]);
+}
+
 inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -592,4 +647,22 @@ extern "C" int srvp_bn_tanh_rows_bwd(const float* dout, const float* out, const 
                                      const float* invstd, float* dz, float* dgamma, float* dbeta, void* stream) {
   bn_tanh_rows_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dout, out, z, rows, C, gamma, mean, invstd, dz, dgamma, dbeta);
   return check_launch("bn_tanh_rows_bwd");
+}
+
+extern "C" int srvp_rows_stats_f32(const float* z, int32_t rows, int32_t C, float* partial, void* stream) {
+  rows_stats_f32_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(z, rows, C, partial);
+  return check_launch("rows_stats_f32");
+}
+
+extern "C" int srvp_bn_tanh_rows_bwd_reduce(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* mean,
+                                            const float* invstd, float* partial, void* stream) {
+  bn_tanh_rows_bwd_reduce_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dout, out, z, rows, C, mean, invstd, partial);
+  return check_launch("bn_tanh_rows_bwd_reduce");
+}
+
+extern "C" int srvp_bn_tanh_rows_bwd_apply(const float* dout, const float* out, const float* z, int32_t rows, int32_t C, const float* gamma,
+                                           const float* mean, const float* invstd, const float* c1, const float* c2, float* dz, void* stream) {
+  const long long total = (long long)rows * C;
+  bn_tanh_rows_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dout, out, z, total, C, gamma, mean, invstd, c1, c2, dz);
+  return check_launch("bn_tanh_rows_bwd_apply");
 }

@@ -143,7 +143,8 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
     conv_l, bn_l = last[0], last[1]
     C = conv_l.in_channels
     gi = 3 * len(plan)
-    dz_last = ops.bn_tanh_rows_bwd(d_hx.contiguous(), c.hx, c.z_last, bn_l.weight, c.st_last, grads[gi + 1], grads[gi + 2])
+    dz_last = ops.bn_tanh_rows_bwd(d_hx.contiguous(), c.hx, c.z_last, bn_l.weight, c.st_last, grads[gi + 1], grads[gi + 2],
+                                   sync=ops.is_sync_bn(bn_l))
     # weight gradient: dWl[co, (y,x,c)] = sum_f dz_last[f, co] * a_last[f, (y,x,c)]
     dwl = torch.zeros(enc.nh, 16, C, dtype=torch.float32, device=dev)
     ops.gemm(dz_last.t(), c.a_last.view(F_, 16 * C).t(), dwl.view(enc.nh, 16 * C), accumulate=True)
@@ -160,7 +161,7 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
             sg, scoff = skip_handle.grads[level]
             kw = dict(skip=sg, skip_coff=scoff, nt=sg.shape[0] // skip_handle.B, B=skip_handle.B, inv_map=skip_handle.inv_map)
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[3 * li + 1], grads[3 * li + 2], da, da_mode, F_, blk.res, blk.res,
-                        blk.cout, **kw)
+                        blk.cout, sync=ops.is_sync_bn(blk.bn), **kw)
         cin_real = blk.cin
         ops.wgrad3x3(c.srcs[li], c.srcs[li].shape[-1], dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_real, grads[3 * li], 'conv')
         if li > 0:
@@ -284,7 +285,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
         blk = plan[li]
         gi = 3 + 3 * li
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[gi + 1], grads[gi + 2], da, da_mode, F_, blk.res, blk.res, blk.cout,
-                        da_coff=da_coff)
+                        da_coff=da_coff, sync=ops.is_sync_bn(blk.bn))
         cin_tot = c.srcs[li].shape[-1]
         ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv')
         wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
@@ -297,7 +298,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     # first_upconv backward
     up_conv, up_bn = dec.first_upconv[0][0], dec.first_upconv[0][1]
     nin, C0 = up_conv.in_channels, up_conv.out_channels
-    dz0 = ops.bn_bwd(c.z0, c.st0, up_bn.weight, grads[1], grads[2], da, SRC_UP2, F_, 4, 4, C0, da_coff=0)
+    dz0 = ops.bn_bwd(c.z0, c.st0, up_bn.weight, grads[1], grads[2], da, SRC_UP2, F_, 4, 4, C0, da_coff=0, sync=ops.is_sync_bn(up_bn))
     d_inp = torch.empty(F_, nin, dtype=torch.float32, device=dev)
     ops.gemm(dz0.view(F_, 16 * C0), c.wp0.view(nin, 16 * C0), d_inp)
     dwp = torch.zeros(nin, 16, C0, dtype=torch.float32, device=dev)

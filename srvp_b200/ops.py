@@ -244,16 +244,28 @@ def transpose_last2(t):
 # ------------------------------------------------------------------------------------------------ batch norm
 class BNState:
     """Per-layer forward affine and saved statistics (all fp32, (C,))."""
-    __slots__ = ('scale', 'shift', 'mean', 'invstd')
+    __slots__ = ('scale', 'shift', 'mean', 'invstd', 'count')
 
     def __init__(self, C, device):
+        self.count = None
         buf = torch.empty(4, C, dtype=torch.float32, device=device)
         self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
+
+
+def is_sync_bn(bn):
+    """True when the container was converted by SyncBatchNorm.convert_sync_batchnorm (reference train.py:283) and a process group is
+    up: batch statistics are then those of the GLOBAL batch (one tiny all-reduce of the per-layer partial sums)."""
+    return isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and torch.distributed.is_initialized() \
+        and torch.distributed.get_world_size() > 1
 
 
 @profiled('bn_finalize')
 def bn_finalize(partial, count, bn, state, training_update=True, eps=1e-5, momentum=0.1):
     """partial: (rows, C, 2). bn: torch.nn.BatchNorm2d parameter container (weight, bias, running_*)."""
+    if is_sync_bn(bn):
+        from . import parallel
+        partial, count = parallel.allreduce_bn_partial(partial, count)
+    state.count = float(count)
     rows, C = partial.shape[0], partial.shape[1]
     rm = bn.running_mean if training_update else None
     rv = bn.running_var if training_update else None
@@ -283,7 +295,7 @@ def channel_stats(z2d):
 
 @profiled('bn_bwd')
 def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_coff=0, skip=None, skip_coff=0, nt=0, B=0,
-           inv_map=None, lrelu=True):
+           inv_map=None, lrelu=True, sync=False):
     """Full BN(train)+LeakyReLU(+pool/upsample) backward. Returns dz (bf16, (frames,H,W,C)); accumulates dgamma/dbeta."""
     dev = z.device
     g = torch.empty(frames, H, W, C, dtype=torch.bfloat16, device=dev)
@@ -299,8 +311,18 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     check(lib().srvp_bn_bwd_reduce(ctypes.byref(a), stream_ptr()), 'bn_bwd_reduce')
     c12 = torch.empty(2, C, dtype=torch.float32, device=dev)
     count = float(frames * H * W)
-    check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(c12[0]), ptr(c12[1]),
-                                    ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
+    if sync:
+        # SyncBatchNorm backward: dgamma / dbeta from the LOCAL sums (DDP averages them), the dx correction from the GLOBAL sums
+        from . import parallel
+        scratch = torch.empty(2, C, dtype=torch.float32, device=dev)
+        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(scratch[0]), ptr(scratch[1]),
+                                        ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
+        tot, gcount = parallel.allreduce_bn_partial(partial, count)
+        check(lib().srvp_bn_bwd_finalize(ptr(tot), c_int(1), c_int(C), ctypes.c_double(gcount), ptr(c12[0]), ptr(c12[1]),
+                                        ptr(None), ptr(None), stream_ptr()), 'bn_bwd_finalize')
+    else:
+        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(c12[0]), ptr(c12[1]),
+                                        ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
     check(lib().srvp_bn_bwd_apply(ctypes.byref(a), ptr(gamma), ptr(c12[0]), ptr(c12[1]), stream_ptr()), 'bn_bwd_apply')
     n = float(frames * H * W * C)
     _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0))
@@ -352,7 +374,12 @@ def bn_tanh_rows_fwd(z, bn, state, training, update_running=True, eps=1e-5, mome
     """z: (rows, C) fp32 -> tanh(bn(z)) fp32. Training: batch statistics; eval: running statistics."""
     rows, C = z.shape
     out = torch.empty_like(z)
-    if not training:
+    if training and is_sync_bn(bn):
+        partial = torch.empty(1, C, 2, dtype=torch.float32, device=z.device)
+        check(lib().srvp_rows_stats_f32(ptr(z), c_int(rows), c_int(C), ptr(partial), stream_ptr()), 'rows_stats_f32')
+        bn_finalize(partial, float(rows), bn, state, training_update=update_running, eps=eps, momentum=momentum)
+        training = False          # the affine is now given: apply it
+    elif not training:
         bn_eval_params(bn, state, eps)
     rm = bn.running_mean if (training and update_running) else None
     rv = bn.running_var if (training and update_running) else None
@@ -363,9 +390,24 @@ def bn_tanh_rows_fwd(z, bn, state, training, update_running=True, eps=1e-5, mome
 
 
 @profiled('bn_tanh_rows_bwd')
-def bn_tanh_rows_bwd(dout, out, z, gamma, state, dgamma, dbeta):
+def bn_tanh_rows_bwd(dout, out, z, gamma, state, dgamma, dbeta, sync=False):
     rows, C = z.shape
     dz = torch.empty_like(z)
+    if sync:
+        from . import parallel
+        dev = z.device
+        partial = torch.empty(1, C, 2, dtype=torch.float32, device=dev)
+        check(lib().srvp_bn_tanh_rows_bwd_reduce(ptr(dout), ptr(out), ptr(z), c_int(rows), c_int(C), ptr(state.mean), ptr(state.invstd),
+                                                ptr(partial), stream_ptr()), 'bn_tanh_rows_bwd_reduce')
+        c12, scratch = torch.empty(2, C, dtype=torch.float32, device=dev), torch.empty(2, C, dtype=torch.float32, device=dev)
+        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(1), c_int(C), ctypes.c_double(float(rows)), ptr(scratch[0]), ptr(scratch[1]),
+                                        ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
+        tot, gcount = parallel.allreduce_bn_partial(partial, float(rows))
+        check(lib().srvp_bn_bwd_finalize(ptr(tot), c_int(1), c_int(C), ctypes.c_double(gcount), ptr(c12[0]), ptr(c12[1]), ptr(None), ptr(None),
+                                        stream_ptr()), 'bn_bwd_finalize')
+        check(lib().srvp_bn_tanh_rows_bwd_apply(ptr(dout), ptr(out), ptr(z), c_int(rows), c_int(C), ptr(gamma), ptr(state.mean),
+                                               ptr(state.invstd), ptr(c12[0]), ptr(c12[1]), ptr(dz), stream_ptr()), 'bn_tanh_rows_bwd_apply')
+        return dz
     check(lib().srvp_bn_tanh_rows_bwd(ptr(dout), ptr(out), ptr(z), c_int(rows), c_int(C), ptr(gamma), ptr(state.mean), ptr(state.invstd),
                                      ptr(dz), ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_tanh_rows_bwd')
     return dz

@@ -33,10 +33,12 @@ def allreduce_mean_(tensors):
 
 
 def allreduce_bn_partial(partial, count):
-    """Sums a (rows, C, 2) partial-statistics tensor over its rows and over all ranks; returns ((1, C, 2) totals, global count)."""
+    """Sums a (rows, C, 2) partial-statistics tensor over its rows and over all ranks; returns ((1, C, 2) totals, global count).
+
+    No host synchronisation: every rank holds the same number of positions (the reference asserts batch_size % n_gpu == 0,
+    train.py:218), so the global count is count * world_size and only the 2C sums travel (one latency-bound all-reduce)."""
     tot = partial.sum(0, keepdim=True)
     if world() == 1:
         return tot, float(count)
-    buf = torch.cat([tot.flatten(), tot.new_tensor([float(count)])])
-    dist.all_reduce(buf)
-    return buf[:-1].view_as(tot), float(buf[-1])
+    dist.all_reduce(tot)
+    return tot, float(count) * world()

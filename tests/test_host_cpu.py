@@ -95,7 +95,7 @@ def _gloo_worker(rank, world, port, q):
     parallel.allreduce_mean_(g)
     # batch-norm statistic exchange: (sum, sumsq, count) partials are summed over ranks
     part = torch.tensor([[[1.0 + rank, 2.0 + rank]]])
-    tot, cnt = parallel.allreduce_bn_partial(part, 5.0 + rank)
+    tot, cnt = parallel.allreduce_bn_partial(part, 5.5)
     q.put((rank, lo, hi, g[0].tolist(), g[1].flatten().tolist(), tot.flatten().tolist(), cnt))
     dist.destroy_process_group()
 
