@@ -23,11 +23,11 @@ namespace srvp {
 
 namespace {
 
-constexpr int kWgThreads = 320;  // warps 0-3 epilogue, 4-7 asynchronous-copy issuers, 8-9 MMA issuers
-constexpr int kCopyThreads = 128;
+constexpr int kWgThreads = 448;  // warps 0-3 epilogue, 4-11 asynchronous-copy issuers, 12-13 MMA issuers
+constexpr int kCopyThreads = 256;
 constexpr int PT = 128;          // pixels (GEMM-K) per pipeline stage
 constexpr int kMaxStages = 4;
-constexpr int kSlots = 3;        // halo-tile rows per copy thread (PH <= 3 * 128)
+constexpr int kSlots = 2;        // halo-tile rows per copy thread (PH <= 2 * 256)
 
 struct PlainDev {
   const __nv_bfloat16* ptr;
@@ -40,6 +40,7 @@ struct WgradDev {
   int halo_on_m;     // 1: activations on the M side (128-block), dz on the N side
   int m_real, n_real;
   int num_mblk, num_nblk, splits;
+  int tap_groups;    // 1: a CTA accumulates all 9 taps; 2: taps [0,5) and [5,9) go to two CTAs (N block of 64 channels)
   int F, H, W, Hp, Wp;
   long long vtotal;
   int steps_total;   // ceil(vtotal / PT)
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
   constexpr int MCH = 16;        // chunks of the M operand (128 channels)
   constexpr int NCH = NBc / 8;   // chunks of the N operand
   constexpr int GM = 4, GN = NCH < 4 ? NCH : 4;
-  constexpr int ACC_COLS = 9 * NBc;
+  constexpr int MAX_TAPS = NBc == 64 ? 5 : 9;   // taps whose accumulators one CTA keeps in TMEM
+  constexpr int ACC_COLS = MAX_TAPS * NBc;
   constexpr int TMEM_COLS = ACC_COLS <= 256 ? 256 : 512;
   extern __shared__ __align__(128) uint8_t smem[];
   const int PH = p.PH;
@@ -129,17 +131,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work assignment: blockIdx -> (split, mblk, nblk)
-  const int pair = blockIdx.x % (p.num_mblk * p.num_nblk);
-  const int split = blockIdx.x / (p.num_mblk * p.num_nblk);
+  // work assignment: blockIdx -> (split, tap group, mblk, nblk); the CTAs of the two tap groups of a piece are neighbours, so
+  // that the tiles they both read are fetched from HBM once
+  const int tg = blockIdx.x % p.tap_groups;
+  const int bidx = blockIdx.x / p.tap_groups;
+  const int pair = bidx % (p.num_mblk * p.num_nblk);
+  const int split = bidx / (p.num_mblk * p.num_nblk);
   const int mblk = pair / p.num_nblk, nblk = pair % p.num_nblk;
+  const int tap0 = (p.tap_groups == 2 && tg == 1) ? 5 : 0;                  // first tap of this CTA
+  const int ntaps = p.tap_groups == 2 ? (tg == 0 ? 5 : 4) : 9;
   const int steps_per = (p.steps_total + p.splits - 1) / p.splits;
   const int step0 = split * steps_per;
   const int step1 = min(p.steps_total, step0 + steps_per);
   const int nsteps = max(0, step1 - step0);
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ asynchronous copies (cp.async, zero-fill for pads)
     const int lt = tid - 128;
     const PlainDev& mop = p.halo_on_m ? p.act : p.dz;
@@ -152,8 +159,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
     const int h_c0 = p.halo_on_m ? m_c0 : n_c0, p_c0 = p.halo_on_m ? n_c0 : m_c0;
     const int h_nch = p.halo_on_m ? m_nch : n_nch, p_nch = p.halo_on_m ? n_nch : m_nch;
     const size_t h_off = p.halo_on_m ? 0 : m_bytes, p_off = p.halo_on_m ? m_bytes : 0;
+    // plain tile: two threads per pixel row, each copying half of the row's chunks; halo tile: whole rows
+    const int prow = lt & (PT - 1), phalf = lt / PT;
+    const int p_nch_lo = (p_nch + 1) / 2;
+    const int p_j0 = phalf == 0 ? 0 : p_nch_lo, p_jn = phalf == 0 ? p_nch_lo : p_nch - p_nch_lo;
     RowPos pr, hr[kSlots];
-    rowpos_init(pr, (long long)step0 * PT + lt, HpWp, p.Wp);
+    rowpos_init(pr, (long long)step0 * PT + prow, HpWp, p.Wp);
 #pragma unroll
     for (int k = 0; k < kSlots; ++k) rowpos_init(hr[k], (long long)step0 * PT - p.Wp - 1 + lt + k * kCopyThreads, HpWp, p.Wp);
     const int df = PT / HpWp, dy = (PT % HpWp) / p.Wp, dx = (PT % HpWp) % p.Wp;
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
       mbar_wait(&empty[st], ((i / kStages) & 1) ^ 1);
       uint8_t* base = smem + st * stage_bytes;
       if ((p.dbg & 3) != 1) {
-        copy_row(pop, p, base + p_off, PT, lt, pr, p_c0, p_nch);
+        copy_row(pop, p, base + p_off + (size_t)p_j0 * PT * 16, PT, prow, pr, p_c0 + p_j0 * 8, p_jn);
 #pragma unroll
         for (int k = 0; k < kSlots; ++k)
           if (lt + k * kCopyThreads < PH) copy_row(hop, p, base + h_off, PH, lt + k * kCopyThreads, hr[k], h_c0, h_nch);
@@ -172,11 +183,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
 #pragma unroll
       for (int k = 0; k < kSlots; ++k) rowpos_advance(hr[k], df, dy, dx, p.Hp, p.Wp);
     }
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------------ MMA issuers: warp 8 -> taps 0-4, warp 9 -> taps 5-8
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ MMA issuers: warps 12 and 13 share this CTA's taps
     // (one thread sustains ~1 MMA / 50 cycles, the tensor core accepts one small-N MMA per 40: two issuers close the gap)
     if (lane == 0 && nsteps > 0) {
-      const int tap_lo = warp == 8 ? 0 : 5, tap_hi = warp == 8 ? 5 : 9;
+      const int half = (ntaps + 1) / 2;
+      const int tap_lo = tap0 + (warp == 12 ? 0 : half), tap_hi = tap0 + (warp == 12 ? half : ntaps);
       constexpr uint32_t idesc = umma_idesc_bf16(128, NBc, 1, 1);
       const uint32_t base = smem_u32(smem);
       for (int i = 0; i < nsteps; ++i) {
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
           const uint64_t ad = ad0 + (p.halo_on_m ? shift : 0u), bd = bd0 + (p.halo_on_m ? 0u : shift);
 #pragma unroll
           for (int kk = 0; kk < PT / 16; ++kk) {
-            if ((p.dbg & 3) != 2) umma_bf16(tmem_base + tap * NBc, ad + kk * 16, bd + kk * 16, idesc, (i | kk) != 0);
+            if ((p.dbg & 3) != 2) umma_bf16(tmem_base + (tap - tap0) * NBc, ad + kk * 16, bd + kk * 16, idesc, (i | kk) != 0);
           }
         }
         umma_commit(&empty[st]);
@@ -208,17 +220,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
       const int cm = mblk * 128 + tid;
       const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        float vals[NBc];
-        if constexpr (NBc == 32) tmem_ld32(acc + tap * NBc, vals);
-        else tmem_ld16(acc + tap * NBc, vals);
-        if (cm < p.m_real) {
-          const int te = p.flip ? 8 - tap : tap;
-          float* dst = p.dw + (long long)cm * p.stride_m + te;
+      for (int t = 0; t < ntaps; ++t) {
+        const int tap = tap0 + t;
+        const int te = p.flip ? 8 - tap : tap;
+        float* dst = p.dw + (long long)cm * p.stride_m + te;
 #pragma unroll
-          for (int n = 0; n < NBc; ++n) {
-            const int cn = nblk * NBc + n;
-            if (cn < p.n_real) atomicAdd(dst + (long long)cn * p.stride_n, vals[n]);
+        for (int c0 = 0; c0 < NBc; c0 += (NBc >= 32 ? 32 : 16)) {
+          float vals[NBc >= 32 ? 32 : 16];
+          if constexpr (NBc >= 32) tmem_ld32(acc + t * NBc + c0, vals);
+          else tmem_ld16(acc + t * NBc + c0, vals);
+          if (cm < p.m_real) {
+#pragma unroll
+            for (int n = 0; n < (NBc >= 32 ? 32 : 16); ++n) {
+              const int cn = nblk * NBc + c0 + n;
+              if (cn < p.n_real) atomicAdd(dst + (long long)cn * p.stride_n, vals[n]);
+            }
           }
         }
       }
@@ -265,12 +281,15 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
     m_ch = a->dz_channels; n_ch = ctot; d.m_real = cout_real; d.n_real = cin_real;
     d.stride_m = a->stride_cout; d.stride_n = a->stride_cin;
   }
-  const int NBc = (n_ch % 32 == 0) ? 32 : 16;
+  // N block: 64 channels with the 9 taps split over two CTAs (a tcgen05.mma with M=128 costs max(N/2, ~40) cycles, so N=64 gets
+  // 1.7x the throughput of N=32 per tensor-core cycle); thin operands (16 channels) keep all taps in one CTA
+  const int NBc = (n_ch % 64 == 0) ? 64 : (n_ch % 32 == 0) ? 32 : 16;
   SRVP_REQUIRE(n_ch % NBc == 0, "wgrad3x3: N-side channels %d not a multiple of 16", n_ch);
+  d.tap_groups = NBc == 64 ? 2 : 1;
   d.num_mblk = (m_ch + 127) / 128;
   d.num_nblk = n_ch / NBc;
   const int sms = num_sms_cached();
-  const int pairs = d.num_mblk * d.num_nblk;
+  const int pairs = d.num_mblk * d.num_nblk * d.tap_groups;
   int splits = (2 * sms) / pairs;  // ~2 waves worth of CTAs keeps the tail short; each CTA is resident alone
   if (splits < 1) splits = 1;
   if (splits > d.steps_total) splits = d.steps_total;
@@ -286,7 +305,11 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   if (smem < 120 * 1024) smem = 120 * 1024;
   SRVP_REQUIRE(smem <= 227 * 1024, "wgrad3x3: shared memory %zu B exceeds 227 KB", smem);
   const int grid = pairs * splits;
-  if (NBc == 32) {
+  if (NBc == 64) {
+    static bool set64 = false;
+    if (!set64) { cudaFuncSetAttribute(wgrad3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set64 = true; }
+    wgrad3x3_kernel<64><<<grid, kWgThreads, smem, stream>>>(d);
+  } else if (NBc == 32) {
     static bool set32 = false;
     if (!set32) { cudaFuncSetAttribute(wgrad3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set32 = true; }
     wgrad3x3_kernel<32><<<grid, kWgThreads, smem, stream>>>(d);
