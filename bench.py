@@ -43,6 +43,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.samples, self.stop_flag, self.max_mhz, self.reasons = [], False, None, set()
+        self.recording = False
         self.nv, self.h = None, None
         try:
             import pynvml
@@ -65,11 +66,13 @@ class ClockSampler(threading.Thread):
                  'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown, 'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
         while not self.stop_flag:
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for name, m in masks.items():
-                    if r & m:
-                        self.reasons.add(name)
+                if self.recording:
+                    self.samples.append(clk)
+                    for name, m in masks.items():
+                        if r & m:
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.05)
@@ -140,11 +143,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)   # NVML is initialised and polled from before the warm-up so that it cannot disturb the timed region
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(xdev)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.recording = True
     launches0 = _lib.lib().srvp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -72,7 +72,7 @@ typedef struct {
 } srvp_conv3x3_args;
 
 /* Number of rows of stats_partial srvp_conv3x3 writes for this geometry / channel count (= its persistent grid size). */
-int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kchannels_per_stage);
+int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kin_total /* sum of src channels */);
 /* N block the kernel uses for a padded output-channel count (16, 64, 128 or 256). */
 int srvp_conv3x3_nblock(int32_t cout_padded);
 int srvp_conv3x3(const srvp_conv3x3_args* args, void* stream);

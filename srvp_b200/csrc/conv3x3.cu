@@ -70,11 +70,15 @@ struct Cfg {
   static constexpr int MBLK = MT / 128;
   static constexpr int WSLOTS = (KCH != 8) ? 2 : (NB >= 256 ? 3 : 4);
   static constexpr int SLOT_BYTES = TPS * KCH * NB * 16;
-  static constexpr int STAGE_PITCH = NB * 2 + 16;  // bytes per staged output row
+  static constexpr int STAGE_COLS = NB < 128 ? NB : 128;  // output columns staged per pass through shared memory
+  static constexpr int STAGE_PITCH = STAGE_COLS * 2 + 16;  // bytes per staged output row
   static constexpr int STAGING_BYTES = (EPI == SRVP_EPI_RAW_BF16) ? 128 * STAGE_PITCH : 0;
   static constexpr int ACC_COLS = MBLK * NB;  // per accumulator stage
-  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  // two accumulator stages (epilogue of tile i overlaps the MMAs of tile i+1) when they fit in the 512 TMEM columns, else one
+  static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int ACC_TOTAL = ACC_STAGES * ACC_COLS;
+  static constexpr int TMEM_COLS = (ACC_TOTAL <= 32) ? 32 : (ACC_TOTAL <= 64) ? 64 : (ACC_TOTAL <= 128) ? 128 : (ACC_TOTAL <= 256) ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(9 % TPS == 0, "taps per slot must divide 9");
   static size_t smem_bytes(int P) {
     return (size_t)kHaloStages * KCH * P * 16 + (size_t)WSLOTS * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 2 * NB * 2 * 4 + 64 * 8 + 16;
@@ -200,8 +204,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
       uint32_t hit = 0, wit = 0, tcount = 0;
       const uint32_t halo_addr = smem_u32(halo), w_addr = smem_u32(wslots);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const int as = tcount & 1;
-        mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
+        const int as = tcount % C::ACC_STAGES;
+        mbar_wait(&acc_empty[as], ((tcount / C::ACC_STAGES) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + as * C::ACC_COLS;
         for (int s = 0; s < p.nstages; ++s, ++hit) {
@@ -262,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mtile = tile / p.num_nblk, nblk = tile % p.num_nblk;
-      const int as = tcount & 1;
-      mbar_wait(&acc_full[as], (tcount >> 1) & 1);
+      const int as = tcount % C::ACC_STAGES;
+      mbar_wait(&acc_full[as], (tcount / C::ACC_STAGES) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
       constexpr int NBAT = (NB + 31) / 32;  // 32-column batches; lane l accumulates column batch*32 + l over this warp's rows
@@ -297,51 +301,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           // every warp stages, reduces and stores its own 32 rows: only warp-level synchronisation is needed
           rowpix[tid] = valid ? ((f * p.H + y) * p.W + x) : -1;
           uint8_t* srow = staging + (size_t)tid * C::STAGE_PITCH;
+          constexpr int BPP = C::STAGE_COLS / 32;  // 32-column batches per staging pass
 #pragma unroll
-          for (int bi = 0; bi < NBAT; ++bi) {
-            float vals[32];
-            tmem_ld32(acc + mb * NB + bi * 32, vals);
-            uint32_t pk[16];
+          for (int ps = 0; ps < NB / C::STAGE_COLS; ++ps) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(vals[2 * q], vals[2 * q + 1]);
+            for (int bb = 0; bb < BPP; ++bb) {
+              const int bi = ps * BPP + bb;
+              float vals[32];
+              tmem_ld32(acc + mb * NB + bi * 32, vals);
+              uint32_t pk[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(srow + bi * 64 + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            if (do_stats) {
-              // statistics of the stored (bf16-rounded) values; pad rows contribute zero
-              float sq[32];
+              for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(vals[2 * q], vals[2 * q + 1]);
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const float2 r = unpack_bf16x2(pk[q]);
-                vals[2 * q] = valid ? r.x : 0.f;
-                vals[2 * q + 1] = valid ? r.y : 0.f;
-                sq[2 * q] = vals[2 * q] * vals[2 * q];
-                sq[2 * q + 1] = vals[2 * q + 1] * vals[2 * q + 1];
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(srow + bb * 64 + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              if (do_stats) {
+                // statistics of the stored (bf16-rounded) values; pad rows contribute zero
+                float sq[32];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const float2 r = unpack_bf16x2(pk[q]);
+                  vals[2 * q] = valid ? r.x : 0.f;
+                  vals[2 * q + 1] = valid ? r.y : 0.f;
+                  sq[2 * q] = vals[2 * q] * vals[2 * q];
+                  sq[2 * q + 1] = vals[2 * q + 1] * vals[2 * q + 1];
+                }
+                s1[bi] += warp_transpose_reduce32(vals, lane);
+                s2[bi] += warp_transpose_reduce32(sq, lane);
               }
-              s1[bi] += warp_transpose_reduce32(vals, lane);
-              s2[bi] += warp_transpose_reduce32(sq, lane);
             }
-          }
-          if (mb == C::MBLK - 1) {
-            tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
-          }
-          __syncwarp();
-          // coalesced store of the valid rows
-          constexpr int LPR = NB / 8;        // lanes per row (16 B each)
-          constexpr int RPI = 32 / LPR;      // rows per warp instruction
-          const int lrow = lane / LPR, lcol = lane % LPR;
-          const int cbase = nblk * NB + lcol * 8;
+            if (mb == C::MBLK - 1 && ps == NB / C::STAGE_COLS - 1) {
+              tc_fence_before();
+              mbar_arrive(&acc_empty[as]);
+            }
+            __syncwarp();
+            // coalesced store of the valid rows
+            constexpr int LPR = C::STAGE_COLS / 8;  // lanes per row (16 B each)
+            constexpr int RPI = 32 / LPR;           // rows per warp instruction
+            const int lrow = lane / LPR, lcol = lane % LPR;
+            const int cbase = nblk * NB + ps * C::STAGE_COLS + lcol * 8;
 #pragma unroll 4
-          for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
-            const int r = r0 + lrow;
-            const int pix = rowpix[r];
-            if (pix >= 0 && cbase < p.cout) {
-              const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
-              *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
+            for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
+              const int r = r0 + lrow;
+              const int pix = rowpix[r];
+              if (pix >= 0 && cbase < p.cout) {
+                const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
+                *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
+              }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       if constexpr (EPI == SRVP_EPI_RAW_BF16) {
@@ -410,10 +419,13 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 struct Choice { int NB, MT; };
-Choice choose(int cout_padded) {
+// kin = total input channels. Wide outputs: deep reductions (kin >= 512) take 256-pixel tiles with a single accumulator stage
+// (halves the L2->SM weight stream, the un-overlapped epilogue is < 10 % of such a tile); shallower ones keep 128-pixel tiles
+// with two accumulator stages so that the epilogue hides behind the next tile.
+Choice choose(int cout_padded, int kin = 0) {
   if (cout_padded <= 16) return {16, 256};
   if (cout_padded == 64) return {64, 512};
-  if (cout_padded % 256 == 0) return {256, 128};
+  if (cout_padded % 256 == 0) return {256, kin >= 512 ? 256 : 128};
   if (cout_padded % 128 == 0) return {128, 256};
   return {64, 512};
 }
@@ -447,9 +459,8 @@ using namespace srvp;
 
 extern "C" int srvp_conv3x3_nblock(int32_t cout_padded) { return choose(cout_padded).NB; }
 
-extern "C" int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kchannels_per_stage) {
-  (void)kchannels_per_stage;
-  const Choice c = choose(cout_padded);
+extern "C" int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kin_total) {
+  const Choice c = choose(cout_padded, kin_total);
   const long long vtotal = (long long)frames * (H + 1) * (W + 2);
   const long long tiles = ((vtotal + c.MT - 1) / c.MT) * (cout_padded / c.NB);
   const int sms = num_sms_cached();
@@ -460,7 +471,9 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRVP_REQUIRE(a != nullptr, "conv3x3: null args");
   SRVP_REQUIRE(a->nsrc == 1 || a->nsrc == 2, "conv3x3: nsrc must be 1 or 2");
-  const Choice ch = choose(a->cout_padded);
+  int kin_total = 0;
+  for (int i = 0; i < a->nsrc; ++i) kin_total += a->src[i].channels;
+  const Choice ch = choose(a->cout_padded, kin_total);
   SRVP_REQUIRE(a->cout_padded % ch.NB == 0 && a->cout <= a->cout_padded, "conv3x3: bad cout %d / padded %d", a->cout, a->cout_padded);
   const int kper = (a->src[0].channels == 16 && a->nsrc == 1) ? 16 : 64;
   ConvDev d{};
@@ -507,7 +520,9 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   switch (ch.NB) {
     case 64: return launch<64, 512, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
     case 128: return launch<128, 256, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
-    case 256: return launch<256, 128, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
+    case 256:
+      if (ch.MT == 256) return launch<256, 256, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
+      return launch<256, 128, 8, 1, SRVP_EPI_RAW_BF16>(d, stream, sms);
     default: break;
   }
   SRVP_REQUIRE(false, "conv3x3: unsupported cout_padded %d", a->cout_padded);

@@ -186,8 +186,7 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
         a.out_cpitch = out.shape[-1] if out_cpitch is None else out_cpitch
         a.out_coff = out_coff
         if stats:
-            kper = 16 if (len(srcs) == 1 and srcs[0].channels == 16) else 64
-            nmt = lib().srvp_conv3x3_num_mtiles(c_int(frames), c_int(H), c_int(W), c_int(cout_padded), c_int(kper))
+            nmt = lib().srvp_conv3x3_num_mtiles(c_int(frames), c_int(H), c_int(W), c_int(cout_padded), c_int(sum(s.channels for s in srcs)))
             stats_partial = torch.empty(nmt, cout, 2, dtype=torch.float32, device=dev)
             a.stats_partial = ptr(stats_partial)
     a_out = None
