@@ -17,8 +17,8 @@
 // traffic for activations is ~1x instead of 9x and the loader has time to apply BN + LeakyReLU + pooling.
 // Outputs at pad positions are computed and discarded (W/(W+2) * H/(H+1) efficiency).
 //
-// Warp roles (persistent CTA, 320 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-7
-// activation loaders, warp 8 MMA issuer (one thread), warp 9 weight TMA-bulk issuer (one thread).
+// Warp roles (persistent CTA, 448 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-11
+// activation loaders, warp 12 MMA issuer (one thread), warp 13 weight TMA-bulk issuer (one thread).
 // TMEM: 2 accumulator stages x (MT/128) x NB fp32 columns, so the epilogue of tile i overlaps tile i+1.
 #include "common.cuh"
 #include "conv_common.cuh"
@@ -28,7 +28,8 @@ namespace srvp {
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 448;   // warps 0-3 epilogue, 4-11 activation loaders, 12 MMA issuer, 13 weight TMA-bulk issuer
+constexpr int kLoaders = 256;
 constexpr int kHaloStages = 2;
 
 struct ConvDev {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < kHaloStages; ++i) { mbar_init(&halo_full[i], 128); mbar_init(&halo_empty[i], 1); }
+    for (int i = 0; i < kHaloStages; ++i) { mbar_init(&halo_full[i], kLoaders); mbar_init(&halo_empty[i], 1); }
     for (int i = 0; i < C::WSLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_mbar_init();
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   const int total_tiles = p.num_mtiles * p.num_nblk;
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ activation loaders
     const int lt = tid - 128;
     uint32_t it = 0;  // halo stage iteration counter
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         const int cloc = cb * KCH * 8;  // first channel of this stage within the source's consumed range
         mbar_wait(&halo_empty[hs], ((it / kHaloStages) & 1) ^ 1);
         uint8_t* hbuf = halo + (size_t)hs * KCH * P * 16;
-        for (int r = lt; r < P; r += 128) {
+        for (int r = lt; r < P; r += kLoaders) {
           const long long vin = vbase + r;
           bool valid = vin >= 0 && vin < p.vtotal;
           int f = 0, y = 0, x = 0;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         mbar_arrive(&halo_full[hs]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NB, 0, 0);
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         umma_commit(&acc_full[as]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ------------------------------------------------------------------ weight loader (TMA bulk copies)
     if (lane == 0) {
       uint32_t wit = 0;
@@ -311,30 +312,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               tmem_ld32(acc + mb * NB + bi * 32, vals);
               uint32_t pk[16];
 #pragma unroll
-              for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(vals[2 * q], vals[2 * q + 1]);
+              for (int q = 0; q < 16; ++q) pk[q] = valid ? pack_bf16x2(vals[2 * q], vals[2 * q + 1]) : 0u;  // pad rows: zeros (never stored)
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<uint4*>(srow + bb * 64 + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-              if (do_stats) {
-                // statistics of the stored (bf16-rounded) values; pad rows contribute zero
-                float sq[32];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  const float2 r = unpack_bf16x2(pk[q]);
-                  vals[2 * q] = valid ? r.x : 0.f;
-                  vals[2 * q + 1] = valid ? r.y : 0.f;
-                  sq[2 * q] = vals[2 * q] * vals[2 * q];
-                  sq[2 * q + 1] = vals[2 * q + 1] * vals[2 * q + 1];
-                }
-                s1[bi] += warp_transpose_reduce32(vals, lane);
-                s2[bi] += warp_transpose_reduce32(sq, lane);
-              }
             }
             if (mb == C::MBLK - 1 && ps == NB / C::STAGE_COLS - 1) {
               tc_fence_before();
               mbar_arrive(&acc_empty[as]);
             }
             __syncwarp();
+            if (do_stats) {
+              // per-channel (sum, sumsq) of the stored bf16 values over this warp's 32 rows: lane l owns the column pairs l, l+32, ...
+              const uint8_t* wrows = staging + (size_t)(warp * 32) * C::STAGE_PITCH;
+#pragma unroll
+              for (int cp = 0; cp < C::STAGE_COLS / 64; ++cp) {
+                float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  const float2 v2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(wrows + (size_t)r * C::STAGE_PITCH + (cp * 32 + lane) * 4));
+                  a0 += v2.x; a1 += v2.y;
+                  q0 = fmaf(v2.x, v2.x, q0); q1 = fmaf(v2.y, v2.y, q1);
+                }
+                const int slot = (ps * (C::STAGE_COLS / 64) + cp) * 2;
+                s1[slot] += a0; s1[slot + 1] += a1;
+                s2[slot] += q0; s2[slot + 1] += q1;
+              }
+            }
             // coalesced store of the valid rows
             constexpr int LPR = C::STAGE_COLS / 8;  // lanes per row (16 B each)
             constexpr int RPI = 32 / LPR;           // rows per warp instruction
@@ -361,9 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           for (int w = 0; w < 4; ++w) {
             if (warp == w) {
 #pragma unroll
-              for (int bi = 0; bi < NBAT; ++bi) {
-                wacc[(bi * 32 + lane) * 2 + 0] += s1[bi];
-                wacc[(bi * 32 + lane) * 2 + 1] += s2[bi];
+              for (int sl = 0; sl < NBAT; ++sl) {
+                const int col = (sl >> 1) * 64 + lane * 2 + (sl & 1);   // pair set, lane's pair, element of the pair
+                wacc[col * 2 + 0] += s1[sl];
+                wacc[col * 2 + 1] += s2[sl];
               }
             }
             named_bar_sync(1, 128);
