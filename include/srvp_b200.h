@@ -41,6 +41,7 @@ int srvp_num_sms(void);
  * ---------------------------------------------------------------------------------------------- */
 enum { SRVP_SRC_DIRECT = 0, SRVP_SRC_POOL2 = 1, SRVP_SRC_UP2 = 2 };
 enum { SRVP_EPI_RAW_BF16 = 0, SRVP_EPI_SIGMOID_NCHW_F32 = 1 };
+enum { SRVP_CONV_MAX_STAGES = 32 }; /* 64-channel K stages per launch (2048 input channels) */
 
 typedef struct {
   const srvp_bf16* ptr; /* NHWC raw tensor; spatial size H,W (DIRECT), 2H,2W (POOL2), H/2,W/2 (UP2) */
@@ -52,6 +53,8 @@ typedef struct {
   int32_t coff;         /* first channel consumed */
   int32_t mode;         /* SRVP_SRC_* */
   int32_t lrelu;        /* 1 = LeakyReLU(0.2) after scale/shift */
+  int32_t row_pitch;    /* DIRECT only: pitch between image rows in pixels (of cpitch elements), 0 = dense (W). Lets a (F,2H,2W,C)
+                           tensor be read as its space-to-depth rows: view (F,H,2W,2C), row_pitch 2W, coff 0 / 2W*C (see 4x4 s2 below) */
 } srvp_conv_src;
 
 typedef struct {
@@ -69,6 +72,11 @@ typedef struct {
   srvp_bf16* a_out;       /* optional: the loader also stores the conv input it computed (BN+LReLU+pool/upsample/concat applied),
                              NHWC (frames,H,W,a_out_cpitch); the weight-gradient kernel reads it back */
   int32_t a_out_cpitch;
+  /* --- extensions used by the 4x4 stride-2 family (DCGAN64, module/conv.py:173-179, :298-305); all zero = plain 3x3 --- */
+  int32_t out_row_pitch;  /* EPI_RAW_BF16: output pixel (f,y,x) is stored at pixel index (f*H+y)*out_row_pitch + x*out_xstride */
+  int32_t out_xstride;    /* (0 = dense: W and 1); with out_coff this addresses one sub-pixel phase of a (F,2H,2W,cout) tensor */
+  int32_t sigmoid_d2s;    /* EPI_SIGMOID_NCHW_F32: column n = (py,px,c) of cout = 4*nc goes to out[f][c][2y+py][2x+px] of (F,nc,2H,2W) */
+  uint16_t tap_mask[SRVP_CONV_MAX_STAGES]; /* per 64-channel K stage: bit (ky*3+kx) set = tap used; 0 = all nine taps */
 } srvp_conv3x3_args;
 
 /* Number of rows of stats_partial srvp_conv3x3 writes for this geometry / channel count (= its persistent grid size). */
@@ -82,6 +90,24 @@ int srvp_conv3x3(const srvp_conv3x3_args* args, void* stream);
  * conv fwd: (Cin*9, 9, 0); conv dgrad: (9, Cin*9, 1); convT fwd: (9, Cout*9, 1); convT dgrad: (Cout*9, 9, 0). */
 int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32_t n_real, int32_t n_padded, int32_t k_real,
                               int32_t k_padded, int64_t stride_n, int64_t stride_k, int32_t flip, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4x4 / stride 2 / pad 1 convolutions of the DCGAN64 encoder/decoder (module/conv.py:173-179 nn.Conv2d(.,.,4,2,1),
+ * :298-305 nn.ConvTranspose2d(.,.,4,2,1)) run on the SAME implicit-GEMM kernel: over the space-to-depth image
+ * S[i][j][(py,px,c)] = X[2i+py][2j+px][c] a 4x4 s2 p1 convolution is a 3x3 s1 p1 convolution in which every
+ * (phase, tap) pair maps to exactly one of the 16 taps or to nothing (ky = 2*tap_y + py - 1 in [0,3]); the transposed
+ * convolution is the same statement per OUTPUT sub-pixel phase (ky = py + 3 - 2*tap_y). Unused taps are skipped with
+ * srvp_conv3x3_args.tap_mask, so no multiply-by-zero work is issued.
+ *   DOWN      k = (py,px,ck) with ck < chan_k (k_real = 4*chan_k), n plain            conv fwd, convT data gradient
+ *   UP_PHASE  n, k plain, one launch per output phase (py,px)                          convT fwd, conv data gradient
+ *   UP_ALL    n = (py,px,cn) with cn < chan_n (n_real = 4*chan_n), k plain, 9 taps     convT fwd when 4*cout <= 16 (last layer)
+ * element (cn, ck, ky, kx) is read from w[cn*stride_n + ck*stride_k + ky*4 + kx].
+ * ---------------------------------------------------------------------------------------------- */
+enum { SRVP_W4_DOWN = 1, SRVP_W4_UP_PHASE = 2, SRVP_W4_UP_ALL = 3 };
+int srvp_pack_conv4x4s2_weights(const float* w, srvp_bf16* wpack, int32_t kind, int32_t chan_n, int32_t n_padded, int32_t chan_k,
+                                int32_t k_padded, int64_t stride_n, int64_t stride_k, int32_t py, int32_t px, void* stream);
+/* tap mask (bit ky*3+kx) of the 3x3 taps a phase uses: DOWN phase of a K stage, or UP_PHASE output phase. */
+int srvp_conv4x4s2_tap_mask(int32_t kind, int32_t py, int32_t px);
 
 /* Weight gradient of the same convolutions (autograd of module/conv.py:198-220, :333-354 via train.py:119):
  * dw[co*stride_cout + ci*stride_cin + (flip ? 8-tap : tap)] += sum_p dz[p, co] * a[p + tap offset, ci], where `a` is
@@ -100,6 +126,10 @@ typedef struct {
   float* dw;
   int64_t stride_cout, stride_cin;
   int32_t flip;
+  /* 4x4 stride-2 family: 0 = 3x3 weight; SRVP_W4_DOWN: the `act` channels are (py,px,c) phases of a space-to-depth tensor;
+   * SRVP_W4_UP_ALL: the `dz` channels are. dw is then a (.,.,4,4) weight: index = co*stride_cout + ci*stride_cin + ky*4+kx with
+   * co/ci the per-phase channel (< phase_channels on the phased side); (phase, tap) pairs without a 4x4 tap are dropped. */
+  int32_t map4, phase_channels;
 } srvp_wgrad3x3_args;
 int srvp_wgrad3x3(const srvp_wgrad3x3_args* args, void* stream);
 
@@ -108,6 +138,9 @@ int srvp_wgrad3x3(const srvp_wgrad3x3_args* args, void* stream);
  * Replaces x.view(nt*bsz, ...) feeding nn.Conv2d (module/srvp.py:176-178) and the x_flat.view of :226.
  * ---------------------------------------------------------------------------------------------- */
 int srvp_nchw_f32_to_nhwc_bf16(const float* x, srvp_bf16* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpad, void* stream);
+/* Same conversion into the space-to-depth image (frames, H/2, W/2, cpad), channel (py*2+px)*C + c = x[f][c][2i+py][2j+px]:
+ * the input of the first DCGAN64 encoder convolution (module/conv.py:174). */
+int srvp_nchw_f32_to_s2d_bf16(const float* x, srvp_bf16* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpad, void* stream);
 int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpitch, void* stream);
 /* Materialises a fused source (BN apply, LeakyReLU, pool/upsample, frame gather) as dense NHWC bf16 (frames,H,W,channels). */
 int srvp_materialize_src(const srvp_conv_src* src, srvp_bf16* out, int32_t frames, int32_t H, int32_t W, void* stream);
@@ -148,6 +181,7 @@ typedef struct {
   float* partial;         /* reduce: out [srvp_bn_bwd_reduce_rows(...)][C][2] */
   int32_t frames, H, W, C;
   int32_t lrelu;
+  int32_t g_s2d;          /* apply: write dz as its space-to-depth image (frames,H/2,W/2,4C), channel (py*2+px)*C + c */
 } srvp_bn_bwd_args;
 int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t da_mode);
 int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* args, void* stream);
@@ -172,6 +206,10 @@ int srvp_bn_tanh_rows_bwd_apply(const float* dout, const float* out, const float
 /* Backward of torch.sigmoid on the decoder output (conv.py:273-274): dz(frames,H,W,16) = dxhat * xhat * (1 - xhat), NCHW fp32 in. */
 int srvp_sigmoid_bwd_nchw_to_nhwc16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,
                                     void* stream);
+
+/* DCGAN64 variant (last layer is ConvTranspose2d(.,nc,4,2,1), conv.py:304): dz16 (frames,H/2,W/2,16), channel (py*2+px)*C + c. */
+int srvp_sigmoid_bwd_nchw_to_s2d16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,
+                                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense GEMM on tcgen05: C[m,n] (+)= act(sum_k A[m,k]*B[n,k] + bias). Element strides; each operand needs one unit stride.

@@ -17,28 +17,32 @@ c_i64 = ctypes.c_int64
 c_ptr = ctypes.c_void_p
 
 
+CONV_MAX_STAGES = 32
+
+
 class ConvSrc(ctypes.Structure):
     _fields_ = [('ptr', c_ptr), ('scale', c_ptr), ('shift', c_ptr), ('frame_map', c_ptr), ('channels', c_int),
-                ('cpitch', c_int), ('coff', c_int), ('mode', c_int), ('lrelu', c_int)]
+                ('cpitch', c_int), ('coff', c_int), ('mode', c_int), ('lrelu', c_int), ('row_pitch', c_int)]
 
 
 class Conv3x3Args(ctypes.Structure):
     _fields_ = [('src', ConvSrc * 2), ('nsrc', c_int), ('wpack', c_ptr), ('frames', c_int), ('H', c_int), ('W', c_int),
                 ('cout', c_int), ('cout_padded', c_int), ('epilogue', c_int), ('out', c_ptr), ('out_cpitch', c_int),
-                ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr), ('a_out', c_ptr), ('a_out_cpitch', c_int)]
+                ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr), ('a_out', c_ptr), ('a_out_cpitch', c_int),
+                ('out_row_pitch', c_int), ('out_xstride', c_int), ('sigmoid_d2s', c_int), ('tap_mask', ctypes.c_uint16 * CONV_MAX_STAGES)]
 
 
 class Wgrad3x3Args(ctypes.Structure):
     _fields_ = [('act', c_ptr), ('act_channels', c_int), ('act_cpitch', c_int), ('act_coff', c_int), ('dz', c_ptr),
                 ('dz_channels', c_int), ('dz_cpitch', c_int), ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
-                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int)]
+                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int), ('map4', c_int), ('phase_channels', c_int)]
 
 
 class BnBwdArgs(ctypes.Structure):
     _fields_ = [('z', c_ptr), ('scale', c_ptr), ('shift', c_ptr), ('mean', c_ptr), ('invstd', c_ptr), ('da', c_ptr),
                 ('da_cpitch', c_int), ('da_coff', c_int), ('da_mode', c_int), ('skip', c_ptr), ('skip_cpitch', c_int),
                 ('skip_coff', c_int), ('nt', c_int), ('B', c_int), ('inv_map', c_ptr), ('g', c_ptr), ('partial', c_ptr),
-                ('frames', c_int), ('H', c_int), ('W', c_int), ('C', c_int), ('lrelu', c_int)]
+                ('frames', c_int), ('H', c_int), ('W', c_int), ('C', c_int), ('lrelu', c_int), ('g_s2d', c_int)]
 
 
 class GemmArgs(ctypes.Structure):
@@ -73,6 +77,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 SRC_DIRECT, SRC_POOL2, SRC_UP2 = 0, 1, 2
 EPI_RAW_BF16, EPI_SIGMOID_NCHW_F32 = 0, 1
+W4_DOWN, W4_UP_PHASE, W4_UP_ALL = 1, 2, 3
 
 _lib = None
 
@@ -96,7 +101,8 @@ def lib():
 # every symbol declared in include/srvp_b200.h
 EXPORTS = [
     'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_launch_count', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
-    'srvp_pack_conv3x3_weights', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16', 'srvp_nhwc_bf16_to_nchw_f32',
+    'srvp_pack_conv3x3_weights', 'srvp_pack_conv4x4s2_weights', 'srvp_conv4x4s2_tap_mask', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16',
+    'srvp_nchw_f32_to_s2d_bf16', 'srvp_sigmoid_bwd_nchw_to_s2d16', 'srvp_nhwc_bf16_to_nchw_f32',
     'srvp_materialize_src', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',

@@ -48,6 +48,10 @@ struct ConvDev {
   float* out_f32;
   __nv_bfloat16* a_out;  // optional copy of the transformed conv input (for the weight-gradient kernel)
   int a_out_cpitch;
+  int out_row_pitch, out_xstride;  // output pixel index = (f*H + y)*out_row_pitch + x*out_xstride (dense: W, 1)
+  int sig_d2s;                     // sigmoid epilogue: columns are (py,px,c) sub-pixel phases of a (F, cout/4, 2H, 2W) image
+  int masked;                      // any K stage with fewer than nine taps (4x4 stride-2 family)
+  uint16_t tap_mask[SRVP_CONV_MAX_STAGES];
 };
 
 // Column sums across the 32 lanes of a warp by recursive halving: lane l ends up with sum over lanes of v[l].
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             if (sd.mode == SRVP_SRC_UP2) {
               base = sd.ptr + (((size_t)fs * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * sd.cpitch + sd.coff + cloc;
             } else {
-              base = sd.ptr + (((size_t)fs * p.H + y) * p.W + x) * sd.cpitch + sd.coff + cloc;
+              base = sd.ptr + (((size_t)fs * p.H + y) * (sd.row_pitch ? sd.row_pitch : p.W) + x) * sd.cpitch + sd.coff + cloc;
             }
             uint4 raw[KCH];
 #pragma unroll
@@ -209,13 +213,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         mbar_wait(&acc_empty[as], ((tcount / C::ACC_STAGES) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + as * C::ACC_COLS;
+        bool fresh = true;  // the first MMA of a tile overwrites the accumulators
         for (int s = 0; s < p.nstages; ++s, ++hit) {
           const int hs = hit % kHaloStages;
           mbar_wait(&halo_full[hs], (hit / kHaloStages) & 1);
           tc_fence_after();
           const uint32_t hbase = halo_addr + hs * KCH * P * 16;
+          const uint32_t tmask = (TPS == 1 && p.masked) ? p.tap_mask[s] : 0x1ffu;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
+            if (!((tmask >> tap) & 1u)) continue;  // 4x4 stride-2 family: this (phase, tap) pair has no weight
+            const bool init = fresh;
+            fresh = false;
             const int ws = wit % C::WSLOTS;
             if (tap % TPS == 0) {
               mbar_wait(&w_full[ws], (wit / C::WSLOTS) & 1);
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               for (int k = 0; k < KCH / 2; ++k) {
                 const uint64_t ad = umma_desc(abase + k * 2 * P * 16, P * 16, 128);
                 const uint64_t bd = umma_desc(wbase + k * 2 * NB * 16, NB * 16, 128);
-                umma_bf16(acc + mb * NB, ad, bd, idesc, (s | tap | k) != 0);
+                umma_bf16(acc + mb * NB, ad, bd, idesc, !(init && k == 0));
               }
             }
             if (tap % TPS == TPS - 1) {
@@ -251,11 +260,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         const int nblk = tile % p.num_nblk;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)nblk * p.nstages * 9 * KCH * NB * 16;
         for (int s = 0; s < p.nstages; ++s) {
-          for (int q = 0; q < 9 / TPS; ++q, ++wit) {
+          const uint32_t tmask = (TPS == 1 && p.masked) ? p.tap_mask[s] : 0x1ffu;
+          for (int q = 0; q < 9 / TPS; ++q) {
+            if (TPS == 1 && !((tmask >> q) & 1u)) continue;
             const int ws = wit % C::WSLOTS;
             mbar_wait(&w_empty[ws], ((wit / C::WSLOTS) & 1) ^ 1);
             mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
             bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
+            ++wit;
           }
         }
       }
@@ -294,13 +306,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             for (int c = 0; c < 16; ++c) {
               if (c < p.cout) {
                 const float sg = 1.f / (1.f + __expf(-vals[c]));
-                p.out_f32[(((size_t)f * p.cout + c) * p.H + y) * p.W + x] = sg;
+                if (p.sig_d2s) {
+                  const int ncr = p.cout >> 2, ph = c / ncr, co = c - ph * ncr;
+                  p.out_f32[(((size_t)f * ncr + co) * (2 * p.H) + 2 * y + (ph >> 1)) * (2 * p.W) + 2 * x + (ph & 1)] = sg;
+                } else {
+                  p.out_f32[(((size_t)f * p.cout + c) * p.H + y) * p.W + x] = sg;
+                }
               }
             }
           }
         } else {
           // every warp stages, reduces and stores its own 32 rows: only warp-level synchronisation is needed
-          rowpix[tid] = valid ? ((f * p.H + y) * p.W + x) : -1;
+          rowpix[tid] = valid ? ((f * p.H + y) * p.out_row_pitch + x * p.out_xstride) : -1;
           uint8_t* srow = staging + (size_t)tid * C::STAGE_PITCH;
           constexpr int BPP = C::STAGE_COLS / 32;  // 32-column batches per staging pass
 #pragma unroll
@@ -423,6 +440,52 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
   reinterpret_cast<uint4*>(wpack)[idx] = o;
 }
 
+// 4x4 / stride 2 / pad 1 weights packed for the same kernel (see include/srvp_b200.h): every (phase, 3x3 tap) pair is one of
+// the 16 taps of the 4x4 kernel or zero. DOWN: ky = 2*ty + py - 1 (phase from k); UP_*: ky = py + 3 - 2*ty (phase from n / fixed).
+__global__ void pack_conv4x4s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpack, int kind, int chan_n, int n_padded,
+                                      int chan_k, int k_padded, long long stride_n, long long stride_k, int py0, int px0, int NB, int KCH) {
+  const long long total = (long long)n_padded * k_padded * 9 / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long t = idx;
+  const int n = (int)(t % NB); t /= NB;
+  const int j = (int)(t % KCH); t /= KCH;
+  const int tap = (int)(t % 9); t /= 9;
+  const int nstages = k_padded / (KCH * 8);
+  const int stage = (int)(t % nstages); t /= nstages;
+  const int nblk = (int)t;
+  const int ng = nblk * NB + n;
+  const int k0 = (stage * KCH + j) * 8;
+  const int ty = tap / 3, tx = tap - 3 * ty;
+  int cn = ng, nph = 0;
+  if (kind == SRVP_W4_UP_ALL) { nph = ng / chan_n; cn = ng - nph * chan_n; }
+  const bool n_ok = (kind == SRVP_W4_UP_ALL) ? (nph < 4) : (ng < chan_n);
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    int ck = k, ky, kx;
+    bool ok = n_ok;
+    if (kind == SRVP_W4_DOWN) {
+      const int ph = k / chan_k;
+      ck = k - ph * chan_k;
+      ok = ok && ph < 4;
+      ky = 2 * ty + (ph >> 1) - 1;
+      kx = 2 * tx + (ph & 1) - 1;
+    } else {
+      const int py = (kind == SRVP_W4_UP_ALL) ? (nph >> 1) : py0, px = (kind == SRVP_W4_UP_ALL) ? (nph & 1) : px0;
+      ok = ok && k < chan_k;
+      ky = py + 3 - 2 * ty;
+      kx = px + 3 - 2 * tx;
+    }
+    ok = ok && ky >= 0 && ky < 4 && kx >= 0 && kx < 4;
+    v[e] = ok ? w[(long long)cn * stride_n + (long long)ck * stride_k + ky * 4 + kx] : 0.f;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(wpack)[idx] = o;
+}
+
 struct Choice { int NB, MT; };
 // kin = total input channels. Wide outputs: deep reductions (kin >= 512) take 256-pixel tiles with a single accumulator stage
 // (halves the L2->SM weight stream, the un-overlapped epilogue is < 10 % of such a tile); shallower ones keep 128-pixel tiles
@@ -491,7 +554,8 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
     SRVP_REQUIRE(s.cpitch % 8 == 0 && s.coff % 8 == 0, "conv3x3: src %d pitch/offset must be multiples of 8", i);
     SRVP_REQUIRE((s.scale == nullptr) == (s.shift == nullptr), "conv3x3: scale and shift must both be given");
     if (s.mode == SRVP_SRC_UP2) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "conv3x3: UP2 needs even output size");
-    d.src[i] = SrcDev{reinterpret_cast<const __nv_bfloat16*>(s.ptr), s.scale, s.shift, s.frame_map, s.channels, s.cpitch, s.coff, s.mode, s.lrelu};
+    d.src[i] = SrcDev{reinterpret_cast<const __nv_bfloat16*>(s.ptr), s.scale, s.shift, s.frame_map, s.channels, s.cpitch, s.coff, s.mode, s.lrelu, s.row_pitch};
+    if (s.row_pitch) SRVP_REQUIRE(s.mode == SRVP_SRC_DIRECT, "conv3x3: row_pitch needs a DIRECT source");
     if (i == 0) d.stages0 = s.channels / kper;
     nst += s.channels / kper;
   }
@@ -511,6 +575,17 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.out_f32 = a->out_f32_nchw;
   d.a_out = reinterpret_cast<__nv_bfloat16*>(a->a_out);
   d.a_out_cpitch = a->a_out_cpitch;
+  d.out_row_pitch = a->out_row_pitch ? a->out_row_pitch : a->W;
+  d.out_xstride = a->out_xstride ? a->out_xstride : 1;
+  d.sig_d2s = a->sigmoid_d2s;
+  SRVP_REQUIRE(nst <= SRVP_CONV_MAX_STAGES, "conv3x3: %d K stages exceed %d", nst, (int)SRVP_CONV_MAX_STAGES);
+  d.masked = 0;
+  for (int i = 0; i < nst; ++i) {
+    d.tap_mask[i] = a->tap_mask[i] ? (a->tap_mask[i] & 0x1ff) : 0x1ff;
+    if (d.tap_mask[i] != 0x1ff) d.masked = 1;
+  }
+  if (d.masked) SRVP_REQUIRE(kper == 64, "conv3x3: tap masks need 64-channel stages");
+  if (d.sig_d2s) SRVP_REQUIRE(a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32 && a->cout % 4 == 0, "conv3x3: sigmoid_d2s needs cout = 4*nc");
   if (a->a_out) SRVP_REQUIRE(a->a_out_cpitch % 8 == 0 && a->a_out_cpitch >= nst * kper, "conv3x3: a_out pitch %d too small", a->a_out_cpitch);
   const int sms = num_sms_cached();
   if (a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32) {
@@ -546,4 +621,34 @@ extern "C" int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32
   pack_conv3x3_kernel<<<(unsigned)blocks, threads, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wpack), n_real, n_padded, k_real, k_padded,
                                                                 stride_n, stride_k, flip, ch.NB, KCH);
   return check_launch("pack_conv3x3");
+}
+
+extern "C" int srvp_pack_conv4x4s2_weights(const float* w, srvp_bf16* wpack, int32_t kind, int32_t chan_n, int32_t n_padded, int32_t chan_k,
+                                           int32_t k_padded, int64_t stride_n, int64_t stride_k, int32_t py, int32_t px, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRVP_REQUIRE(kind == SRVP_W4_DOWN || kind == SRVP_W4_UP_PHASE || kind == SRVP_W4_UP_ALL, "pack4x4: bad kind %d", kind);
+  const Choice ch = choose(n_padded);
+  SRVP_REQUIRE(n_padded % ch.NB == 0, "pack4x4: n_padded %d not a multiple of block %d", n_padded, ch.NB);
+  const int KCH = (k_padded == 16) ? 2 : 8;
+  SRVP_REQUIRE(k_padded % (KCH * 8) == 0, "pack4x4: k_padded %d", k_padded);
+  SRVP_REQUIRE((kind == SRVP_W4_UP_ALL ? 4 * chan_n : chan_n) <= n_padded, "pack4x4: n channels %d exceed padded %d", chan_n, n_padded);
+  SRVP_REQUIRE((kind == SRVP_W4_DOWN ? 4 * chan_k : chan_k) <= k_padded, "pack4x4: k channels %d exceed padded %d", chan_k, k_padded);
+  SRVP_REQUIRE(py >= 0 && py < 2 && px >= 0 && px < 2, "pack4x4: bad phase");
+  const long long total = (long long)n_padded * k_padded * 9 / 8;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  pack_conv4x4s2_kernel<<<(unsigned)blocks, threads, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wpack), kind, chan_n, n_padded, chan_k,
+                                                                  k_padded, stride_n, stride_k, py, px, ch.NB, KCH);
+  return check_launch("pack_conv4x4s2");
+}
+
+extern "C" int srvp_conv4x4s2_tap_mask(int32_t kind, int32_t py, int32_t px) {
+  int mask = 0;
+  for (int ty = 0; ty < 3; ++ty)
+    for (int tx = 0; tx < 3; ++tx) {
+      const int ky = (kind == SRVP_W4_DOWN) ? 2 * ty + py - 1 : py + 3 - 2 * ty;
+      const int kx = (kind == SRVP_W4_DOWN) ? 2 * tx + px - 1 : px + 3 - 2 * tx;
+      if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4) mask |= 1 << (ty * 3 + tx);
+    }
+  return mask;
 }

@@ -12,6 +12,7 @@ struct SrcDev {
   const float* shift;
   const int* frame_map;
   int channels, cpitch, coff, mode, lrelu;
+  int row_pitch;  // DIRECT: pixels between image rows (0 = W)
 };
 
 __device__ __forceinline__ uint4 transform8(uint4 raw, const float* __restrict__ scale, const float* __restrict__ shift, int lrelu_flag) {
@@ -79,7 +80,7 @@ __device__ __forceinline__ uint4 load_src8(const SrcDev& sd, int f, int y, int x
   if (sd.mode == SRVP_SRC_UP2) {
     base = sd.ptr + (((size_t)fs * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * sd.cpitch + sd.coff + c;
   } else {
-    base = sd.ptr + (((size_t)fs * H + y) * W + x) * sd.cpitch + sd.coff + c;
+    base = sd.ptr + (((size_t)fs * H + y) * (sd.row_pitch ? sd.row_pitch : W) + x) * sd.cpitch + sd.coff + c;
   }
   return transform8(__ldg(reinterpret_cast<const uint4*>(base)), sc, sh, sd.lrelu);
 }

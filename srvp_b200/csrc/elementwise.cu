@@ -30,6 +30,30 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
   }
 }
 
+// NCHW fp32 -> space-to-depth NHWC bf16: out[f][i][j][(py*2+px)*C + c] = x[f][c][2i+py][2j+px], zero padded to Cpad channels.
+__global__ void nchw_to_s2d_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long npix_total, int C, int H, int W, int Cpad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over (f, i, j) of the half-resolution image
+  if (i >= npix_total) return;
+  const int Wo = W / 2, Ho = H / 2;
+  const int xj = (int)(i % Wo);
+  const long long t = i / Wo;
+  const int yi = (int)(t % Ho);
+  const long long f = t / Ho;
+  const float* src = x + f * C * H * W;
+  __nv_bfloat16* dst = out + i * Cpad;
+  for (int c0 = 0; c0 < Cpad; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = c0 + e, ph = k / C, c = k - ph * C;
+      v[e] = (ph < 4) ? __ldg(src + ((long long)c * H + 2 * yi + (ph >> 1)) * W + 2 * xj + (ph & 1)) : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + c0) = o;
+  }
+}
+
 // NHWC bf16 (pitch Cp) -> NCHW fp32, C real channels. One thread per (f, c, pixel); coalesced on the write side.
 __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long total, int C, int HW, int Cp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,6 +161,7 @@ struct BnBwdDev {
   float* partial;              // out: [gridDim.x][C][2] = (sum g, sum g*xhat)
   int F, H, W, C;
   int lrelu;
+  int g_s2d;                   // apply: dz written as its space-to-depth image [F,H/2,W/2,4C]
 };
 
 __device__ __forceinline__ void unpack8(uint4 r, float* v) {
@@ -282,7 +307,11 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
             s2[e] = fmaf(gg, fmaf(zv[q][e], ka[e], -kb[e]), s2[e]);
           }
         }
-        if (APPLY) *reinterpret_cast<uint4*>(p.g + (((size_t)f * p.H + y) * p.W + x) * p.C + c0) = pack8(o);
+        if (APPLY) {
+          const size_t gi = p.g_s2d ? ((((size_t)f * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1))) * p.C
+                                    : (((size_t)f * p.H + y) * p.W + x) * p.C;
+          *reinterpret_cast<uint4*>(p.g + gi + c0) = pack8(o);
+        }
       }
     }
   }
@@ -352,6 +381,33 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ dx, const float* __
       v[c] = __ldg(dx + idx) * s * (1.f - s);
     } else {
       v[c] = 0.f;
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+  dst[0] = pack8(v);
+  dst[1] = pack8(v + 8);
+}
+
+// Space-to-depth variant: out[f][i][j][(py*2+px)*C + c] = (dxhat * xhat * (1 - xhat))[f][c][2i+py][2j+px], 4C <= 16 channels.
+__global__ void sigmoid_bwd_s2d_kernel(const float* __restrict__ dx, const float* __restrict__ xh, __nv_bfloat16* __restrict__ out, long long npix, int C,
+                                       int H, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (f, i, j) of the half-resolution image
+  if (i >= npix) return;
+  const int Wo = W / 2, Ho = H / 2;
+  const int xj = (int)(i % Wo);
+  const long long t = i / Wo;
+  const int yi = (int)(t % Ho);
+  const long long f = t / Ho;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int ph = k / C, c = k - ph * C;
+    if (ph < 4) {
+      const long long idx = ((f * C + c) * H + 2 * yi + (ph >> 1)) * W + 2 * xj + (ph & 1);
+      const float sg = __ldg(xh + idx);
+      v[k] = __ldg(dx + idx) * sg * (1.f - sg);
+    } else {
+      v[k] = 0.f;
     }
   }
   uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
@@ -526,6 +582,14 @@ extern "C" int srvp_nchw_f32_to_nhwc_bf16(const float* x, srvp_bf16* out, int32_
   return check_launch("nchw_to_nhwc");
 }
 
+extern "C" int srvp_nchw_f32_to_s2d_bf16(const float* x, srvp_bf16* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpad,
+                                         void* stream) {
+  SRVP_REQUIRE(cpad % 8 == 0 && cpad >= 4 * C && H % 2 == 0 && W % 2 == 0, "nchw_to_s2d: bad channel padding %d for 4*%d, or odd size", cpad, C);
+  const long long npix = (long long)frames * (H / 2) * (W / 2);
+  nchw_to_s2d_bf16_kernel<<<blocks_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), npix, C, H, W, cpad);
+  return check_launch("nchw_to_s2d");
+}
+
 extern "C" int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpitch,
                                           void* stream) {
   const long long total = (long long)frames * C * H * W;
@@ -535,7 +599,7 @@ extern "C" int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32
 
 extern "C" int srvp_materialize_src(const srvp_conv_src* s, srvp_bf16* out, int32_t frames, int32_t H, int32_t W, void* stream) {
   SRVP_REQUIRE(s != nullptr && s->channels % 8 == 0, "materialize_src: bad source");
-  SrcDev sd{reinterpret_cast<const __nv_bfloat16*>(s->ptr), s->scale, s->shift, s->frame_map, s->channels, s->cpitch, s->coff, s->mode, s->lrelu};
+  SrcDev sd{reinterpret_cast<const __nv_bfloat16*>(s->ptr), s->scale, s->shift, s->frame_map, s->channels, s->cpitch, s->coff, s->mode, s->lrelu, s->row_pitch};
   const long long total = (long long)frames * H * W * (s->channels / 8);
   materialize_src_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(sd, reinterpret_cast<__nv_bfloat16*>(out), total, H, W, s->channels);
   return check_launch("materialize_src");
@@ -592,6 +656,8 @@ static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gam
   d.g = reinterpret_cast<__nv_bfloat16*>(a->g);
   d.partial = a->partial;
   d.F = a->frames; d.H = a->H; d.W = a->W; d.C = a->C; d.lrelu = a->lrelu;
+  d.g_s2d = a->g_s2d;
+  if (a->g_s2d) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "bn_bwd: space-to-depth output needs even size");
   const bool pooled = a->da_mode == SRVP_SRC_POOL2;
   if (pooled || a->da_mode == SRVP_SRC_UP2) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0 || !pooled, "bn_bwd: pooled mode needs even size");
   const long long items = pooled ? (long long)a->frames * (a->H / 2) * (a->W / 2) : (long long)a->frames * a->H * a->W;
@@ -626,6 +692,14 @@ extern "C" int srvp_sigmoid_bwd_nchw_to_nhwc16(const float* dxhat, const float* 
   const long long npix = (long long)frames * H * W;
   sigmoid_bwd_kernel<<<blocks_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(dxhat, xhat, reinterpret_cast<__nv_bfloat16*>(dz16), npix, C, H * W);
   return check_launch("sigmoid_bwd");
+}
+
+extern "C" int srvp_sigmoid_bwd_nchw_to_s2d16(const float* dxhat, const float* xhat, srvp_bf16* dz16, int32_t frames, int32_t C, int32_t H, int32_t W,
+                                              void* stream) {
+  SRVP_REQUIRE(4 * C <= 16 && H % 2 == 0 && W % 2 == 0, "sigmoid_bwd_s2d: 4*C=%d > 16 or odd size", 4 * C);
+  const long long npix = (long long)frames * (H / 2) * (W / 2);
+  sigmoid_bwd_s2d_kernel<<<blocks_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(dxhat, xhat, reinterpret_cast<__nv_bfloat16*>(dz16), npix, C, H, W);
+  return check_launch("sigmoid_bwd_s2d");
 }
 
 extern "C" int srvp_transpose_last2_f32(const float* in, float* out, int32_t A, int32_t B, int32_t C, void* stream) {

@@ -47,6 +47,8 @@ struct WgradDev {
   float* dw;
   long long stride_m, stride_n;
   int flip;
+  int map4;          // 0: 3x3 weight; SRVP_W4_DOWN / SRVP_W4_UP_ALL: (.,.,4,4) weight of a stride-2 (transposed) convolution, the act / dz
+  int cph;           //    channels being (py,px,c) phases of a space-to-depth tensor with cph channels per phase
   int PH;            // rows of the halo operand tile = PT + 2*Wp + 2
   int nstg;          // pipeline stages (2..4, as many as fit in shared memory)
   int dbg;           // development only: 1 = skip loads, 2 = skip MMAs
@@ -219,11 +221,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
       tc_fence_after();
       const int cm = mblk * 128 + tid;
       const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
+      // 4x4 stride-2 family: one operand's channels are (phase, channel); (phase, tap) selects one of the 16 taps or nothing
+      const bool m_is_act = p.halo_on_m != 0;
+      const bool m_phased = p.map4 != 0 && ((p.map4 == SRVP_W4_DOWN) == m_is_act);
+      int m_ph = 0, m_c = cm;
+      if (m_phased) { m_ph = cm / p.cph; m_c = cm - m_ph * p.cph; }
 #pragma unroll 1
       for (int t = 0; t < ntaps; ++t) {
         const int tap = tap0 + t;
         const int te = p.flip ? 8 - tap : tap;
-        float* dst = p.dw + (long long)cm * p.stride_m + te;
+        const int ty = tap / 3, tx = tap - 3 * ty;
+        float* dst = p.dw + (long long)m_c * p.stride_m + (p.map4 ? 0 : te);
 #pragma unroll
         for (int c0 = 0; c0 < NBc; c0 += (NBc >= 32 ? 32 : 16)) {
           float vals[NBc >= 32 ? 32 : 16];
@@ -233,7 +241,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
 #pragma unroll
             for (int n = 0; n < (NBc >= 32 ? 32 : 16); ++n) {
               const int cn = nblk * NBc + c0 + n;
-              if (cn < p.n_real) atomicAdd(dst + (long long)cn * p.stride_n, vals[n]);
+              if (cn >= p.n_real) continue;
+              if (p.map4 == 0) {
+                atomicAdd(dst + (long long)cn * p.stride_n, vals[n]);
+              } else {
+                int ph = m_ph, n_c = cn;
+                if (!m_phased) { ph = cn / p.cph; n_c = cn - ph * p.cph; }
+                const int py = ph >> 1, px = ph & 1;
+                const int ky = (p.map4 == SRVP_W4_DOWN) ? 2 * ty + py - 1 : py + 3 - 2 * ty;
+                const int kx = (p.map4 == SRVP_W4_DOWN) ? 2 * tx + px - 1 : px + 3 - 2 * tx;
+                if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4) atomicAdd(dst + (long long)n_c * p.stride_n + ky * 4 + kx, vals[n]);
+              }
             }
           }
         }
@@ -269,6 +287,9 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   d.PH = PT + 2 * d.Wp + 2;
   d.dw = a->dw;
   d.flip = a->flip & 1;
+  d.map4 = a->map4;
+  d.cph = a->phase_channels;
+  SRVP_REQUIRE(a->map4 == 0 || ((a->map4 == SRVP_W4_DOWN || a->map4 == SRVP_W4_UP_ALL) && a->phase_channels > 0), "wgrad3x3: bad map4 %d", a->map4);
   d.dbg = a->flip >> 8;
   // which operand fills the 128-wide M side
   const int cout_real = a->cout, cin_real = a->cin;

@@ -84,7 +84,7 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         from .. import ops
         skips = []
         for (z, st, C, res) in handle.levels:
-            src = ops.Src(z, C, st.scale, st.shift, handle.frame_map, 0, 0, True)
+            src = ops.Src(z, C, st.scale if st is not None else None, st.shift if st is not None else None, handle.frame_map, 0, 0, True)
             skips.append(ops.nhwc_to_nchw_f32(ops.materialize(src, x.shape[1], res, res), C))
         return hx, skips
 

@@ -63,6 +63,7 @@ class Src:
     coff: int = 0
     mode: int = _lib.SRC_DIRECT
     lrelu: bool = False
+    row_pitch: int = 0                         # DIRECT only: pixels between image rows (0 = dense), see srvp_conv_src.row_pitch
 
 
 def conv3x3_kind_strides(kind, cout, cin):
@@ -122,10 +123,32 @@ def _fill_src(cs, s):
     cs.coff = s.coff
     cs.mode = s.mode
     cs.lrelu = int(s.lrelu)
+    cs.row_pitch = s.row_pitch
+
+
+def tap_mask4(kind, py, px):
+    """3x3 taps (bit ky*3+kx) a sub-pixel phase of the 4x4 stride-2 family uses (srvp_conv4x4s2_tap_mask)."""
+    return lib().srvp_conv4x4s2_tap_mask(c_int(kind), c_int(py), c_int(px))
+
+
+@profiled('pack_conv4x4s2')
+def pack_conv4x4s2(weight, kind, chan_n, chan_k, stride_n, stride_k, py=0, px=0, n_offset=0):
+    """fp32 (.,.,4,4) weight of a stride-2 pad-1 (transposed) convolution -> packed bf16 B operand of the 3x3 kernel run over the
+    space-to-depth image (include/srvp_b200.h). n_offset: first n channel (for output-channel splits)."""
+    assert weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
+    n_real = 4 * chan_n if kind == _lib.W4_UP_ALL else chan_n
+    k_real = 4 * chan_k if kind == _lib.W4_DOWN else chan_k
+    n_pad, k_pad = padded_n(n_real), padded_k(k_real)
+    out = torch.empty(n_pad * k_pad * 9, dtype=torch.bfloat16, device=weight.device)
+    wptr = ctypes.c_void_p(weight.data_ptr() + 4 * n_offset * stride_n)
+    check(lib().srvp_pack_conv4x4s2_weights(wptr, ptr(out), c_int(kind), c_int(chan_n), c_int(n_pad), c_int(chan_k), c_int(k_pad),
+                                           c_i64(stride_n), c_i64(stride_k), c_int(py), c_int(px), stream_ptr()), 'pack_conv4x4s2_weights')
+    return out
 
 
 @profiled('wgrad3x3')
-def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0):
+def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0, map4=0, phase_channels=0,
+             strides=None):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
 
     act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...)."""
@@ -138,35 +161,37 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
     a.frames, a.H, a.W = frames, H, W
     a.cout, a.cin = cout, cin
     a.dw = ptr(dw)
-    if kind == 'conv':
+    if strides is not None:          # 4x4 stride-2 family: (stride of the dz-side channel, stride of the act-side channel) in dw
+        a.stride_cout, a.stride_cin, a.flip = strides[0], strides[1], 0
+    elif kind == 'conv':
         a.stride_cout, a.stride_cin, a.flip = cin * 9, 9, 0
     else:
         a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
+    a.map4, a.phase_channels = map4, phase_channels
     check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
-    _account(2.0 * frames * H * W * cout * cin * 9, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel())
+    _account(2.0 * frames * H * W * cout * cin * (4 if map4 else 9), 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel())
     return dw
 
 
 @profiled('conv3x3')
 def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None,
-            save_input=False):
-    """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None)."""
+            save_input=False, tap_masks=None, out_row_pitch=0, out_xstride=0, stats_out=None, a_out=None, sigmoid_d2s=False, taps=9):
+    """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None).
+
+    4x4 stride-2 family (DCGAN64): tap_masks = one 9-bit mask per 64-channel K stage (or one int for all stages), out_row_pitch /
+    out_xstride / out_coff address one sub-pixel phase of the output, stats_out / a_out are caller-allocated (shared by the four
+    phase launches), sigmoid_d2s scatters the (py,px,c) columns of the last layer to the NCHW image."""
     a = _lib.Conv3x3Args()
     a.nsrc = len(srcs)
-    keep = []
     for i, s in enumerate(srcs):
-        assert s.tensor.dtype == torch.bfloat16
-        cs = a.src[i]
-        cs.ptr = ptr(s.tensor)
-        cs.scale = ptr(s.scale)
-        cs.shift = ptr(s.shift)
-        cs.frame_map = ptr(s.frame_map)
-        cs.channels = s.channels
-        cs.cpitch = s.tensor.shape[-1]
-        cs.coff = s.coff
-        cs.mode = s.mode
-        cs.lrelu = int(s.lrelu)
-        keep.append(s)
+        _fill_src(a.src[i], s)
+    nstages = sum(s.channels for s in srcs) // 64
+    if tap_masks is not None:
+        masks = [tap_masks] * nstages if isinstance(tap_masks, int) else list(tap_masks)
+        assert len(masks) == nstages, (len(masks), nstages)
+        for i, m in enumerate(masks):
+            a.tap_mask[i] = m
+    a.out_row_pitch, a.out_xstride, a.sigmoid_d2s = out_row_pitch, out_xstride, int(sigmoid_d2s)
     dev = srcs[0].tensor.device
     cout_padded = padded_n(cout)
     a.wpack = ptr(wpack)
@@ -176,7 +201,7 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
     if sigmoid_nchw:
         a.epilogue = _lib.EPI_SIGMOID_NCHW_F32
         if out is None:
-            out = torch.empty(frames, cout, H, W, dtype=torch.float32, device=dev)
+            out = torch.empty((frames, cout // 4, 2 * H, 2 * W) if sigmoid_d2s else (frames, cout, H, W), dtype=torch.float32, device=dev)
         a.out_f32_nchw = ptr(out)
     else:
         a.epilogue = _lib.EPI_RAW_BF16
@@ -185,24 +210,42 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
         a.out = ptr(out)
         a.out_cpitch = out.shape[-1] if out_cpitch is None else out_cpitch
         a.out_coff = out_coff
-        if stats:
-            nmt = lib().srvp_conv3x3_num_mtiles(c_int(frames), c_int(H), c_int(W), c_int(cout_padded), c_int(sum(s.channels for s in srcs)))
+        if stats_out is not None:
+            stats_partial = stats_out
+            a.stats_partial = ptr(stats_partial)
+        elif stats:
+            nmt = conv3x3_stats_rows(frames, H, W, cout, sum(s.channels for s in srcs))
             stats_partial = torch.empty(nmt, cout, 2, dtype=torch.float32, device=dev)
             a.stats_partial = ptr(stats_partial)
-    a_out = None
-    if save_input:
+    if save_input and a_out is None:
         a_out = torch.empty(frames, H, W, sum(s.channels for s in srcs), dtype=torch.bfloat16, device=dev)
+    if save_input:
         a.a_out, a.a_out_cpitch = ptr(a_out), a_out.shape[-1]
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
     cin_real = cin_real if cin_real is not None else sum(s.channels for s in srcs)
-    obytes = out.numel() * out.element_size()
-    _account(2.0 * frames * H * W * cout * cin_real * 9, sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
+    obytes = (out.numel() * out.element_size()) if not out_xstride else 2.0 * frames * H * W * cout
+    _account(2.0 * frames * H * W * cout * cin_real * taps, sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
     if save_input:
         return out, stats_partial, a_out
     return out, stats_partial
 
 
+def conv3x3_stats_rows(frames, H, W, cout, kin_total):
+    """Rows of the per-CTA statistics a conv3x3 launch of this geometry writes."""
+    return lib().srvp_conv3x3_num_mtiles(c_int(frames), c_int(H), c_int(W), c_int(padded_n(cout)), c_int(kin_total))
+
+
 # ------------------------------------------------------------------------------------------------ layout
+@profiled('nchw_to_s2d_bf16')
+def nchw_to_s2d_bf16(x, cpad):
+    """(frames, C, H, W) fp32 -> space-to-depth (frames, H/2, W/2, cpad) bf16, channel (py*2+px)*C + c."""
+    F_, C, H, W = x.shape
+    out = torch.empty(F_, H // 2, W // 2, cpad, dtype=torch.bfloat16, device=x.device)
+    check(lib().srvp_nchw_f32_to_s2d_bf16(ptr(x), ptr(out), c_int(F_), c_int(C), c_int(H), c_int(W), c_int(cpad), stream_ptr()),
+          'nchw_to_s2d')
+    return out
+
+
 @profiled('nchw_to_nhwc_bf16')
 def nchw_to_nhwc_bf16(x, cpad):
     """(frames, C, H, W) fp32 -> (frames, H, W, cpad) bf16, zero padded channels."""
@@ -294,10 +337,11 @@ def channel_stats(z2d):
 
 @profiled('bn_bwd')
 def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_coff=0, skip=None, skip_coff=0, nt=0, B=0,
-           inv_map=None, lrelu=True, sync=False):
-    """Full BN(train)+LeakyReLU(+pool/upsample) backward. Returns dz (bf16, (frames,H,W,C)); accumulates dgamma/dbeta."""
+           inv_map=None, lrelu=True, sync=False, g_s2d=False):
+    """Full BN(train)+LeakyReLU(+pool/upsample) backward. Returns dz (bf16, (frames,H,W,C), or its space-to-depth image
+    (frames,H/2,W/2,4C) with g_s2d); accumulates dgamma/dbeta."""
     dev = z.device
-    g = torch.empty(frames, H, W, C, dtype=torch.bfloat16, device=dev)
+    g = torch.empty((frames, H // 2, W // 2, 4 * C) if g_s2d else (frames, H, W, C), dtype=torch.bfloat16, device=dev)
     rows = lib().srvp_bn_bwd_reduce_rows(c_int(frames), c_int(H), c_int(W), c_int(da_mode))
     partial = torch.empty(rows, C, 2, dtype=torch.float32, device=dev)
     a = _lib.BnBwdArgs()
@@ -306,7 +350,7 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     if skip is not None:
         a.skip, a.skip_cpitch, a.skip_coff, a.nt, a.B, a.inv_map = ptr(skip), skip.shape[-1], skip_coff, nt, B, ptr(inv_map)
     a.g, a.partial = ptr(g), ptr(partial)
-    a.frames, a.H, a.W, a.C, a.lrelu = frames, H, W, C, int(lrelu)
+    a.frames, a.H, a.W, a.C, a.lrelu, a.g_s2d = frames, H, W, C, int(lrelu), int(g_s2d)
     check(lib().srvp_bn_bwd_reduce(ctypes.byref(a), stream_ptr()), 'bn_bwd_reduce')
     c12 = torch.empty(2, C, dtype=torch.float32, device=dev)
     count = float(frames * H * W)
@@ -326,6 +370,40 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     n = float(frames * H * W * C)
     _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0))
     return g
+
+
+_IDENT = {}
+
+
+@profiled('lrelu_bwd')
+def lrelu_bwd(z, da, frames, H, W, C, *, skip=None, skip_coff=0, nt=0, B=0, inv_map=None):
+    """Backward of a bare LeakyReLU (no batch-norm: first DCGAN64 encoder block, module/conv.py:174): dz = lrelu'(z) * (da + skip
+    gradient). Runs the apply pass of the BN backward kernel with an identity affine."""
+    dev = z.device
+    key = (dev, C)
+    if key not in _IDENT:
+        _IDENT[key] = (torch.ones(C, dtype=torch.float32, device=dev), torch.zeros(C, dtype=torch.float32, device=dev))
+    one, zero = _IDENT[key]
+    g = torch.empty(frames, H, W, C, dtype=torch.bfloat16, device=dev)
+    a = _lib.BnBwdArgs()
+    a.z, a.scale, a.shift, a.mean, a.invstd = ptr(z), ptr(one), ptr(zero), ptr(zero), ptr(one)
+    a.da, a.da_cpitch, a.da_coff, a.da_mode = ptr(da), da.shape[-1], 0, _lib.SRC_DIRECT
+    if skip is not None:
+        a.skip, a.skip_cpitch, a.skip_coff, a.nt, a.B, a.inv_map = ptr(skip), skip.shape[-1], skip_coff, nt, B, ptr(inv_map)
+    a.g = ptr(g)
+    a.frames, a.H, a.W, a.C, a.lrelu = frames, H, W, C, 1
+    check(lib().srvp_bn_bwd_apply(ctypes.byref(a), ptr(one), ptr(zero), ptr(zero), stream_ptr()), 'bn_bwd_apply')
+    return g
+
+
+@profiled('sigmoid_bwd')
+def sigmoid_bwd_s2d(dxhat, xhat):
+    """(frames, C, H, W) fp32 x2 -> dz (frames, H/2, W/2, 16) bf16, channel (py*2+px)*C + c (last DCGAN64 decoder layer)."""
+    F_, C, H, W = xhat.shape
+    out = torch.empty(F_, H // 2, W // 2, 16, dtype=torch.bfloat16, device=xhat.device)
+    check(lib().srvp_sigmoid_bwd_nchw_to_s2d16(ptr(dxhat), ptr(xhat), ptr(out), c_int(F_), c_int(C), c_int(H), c_int(W), stream_ptr()),
+          'sigmoid_bwd_s2d')
+    return out
 
 
 @profiled('sigmoid_bwd')
