@@ -77,6 +77,12 @@ typedef struct {
   int32_t out_xstride;    /* (0 = dense: W and 1); with out_coff this addresses one sub-pixel phase of a (F,2H,2W,cout) tensor */
   int32_t sigmoid_d2s;    /* EPI_SIGMOID_NCHW_F32: column n = (py,px,c) of cout = 4*nc goes to out[f][c][2y+py][2x+px] of (F,nc,2H,2W) */
   uint16_t tap_mask[SRVP_CONV_MAX_STAGES]; /* per 64-channel K stage: bit (ky*3+kx) set = tap used; 0 = all nine taps */
+  /* --- convolution over torch.cat([h, skip], 1) (conv.py:270) split as conv_h(h) + conv_s(skip): the skip features are the same
+   * for every time step of a video (srvp.py:222-223), so conv_s runs once per VIDEO (fp32 result, out_raw_f32) and the per-frame
+   * launch adds it to its accumulators before rounding / statistics (add_f32, frame f uses row f % add_frames) --- */
+  const float* add_f32;   /* optional (add_frames, H, W, cout) fp32 */
+  int32_t add_frames;
+  float* out_raw_f32;     /* optional (frames, H, W, cout) fp32 copy of the raw result; `out` may then be NULL */
 } srvp_conv3x3_args;
 
 /* Number of rows of stats_partial srvp_conv3x3 writes for this geometry / channel count (= its persistent grid size). */
@@ -142,6 +148,9 @@ int srvp_nchw_f32_to_nhwc_bf16(const float* x, srvp_bf16* out, int32_t frames, i
  * the input of the first DCGAN64 encoder convolution (module/conv.py:174). */
 int srvp_nchw_f32_to_s2d_bf16(const float* x, srvp_bf16* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpad, void* stream);
 int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32_t frames, int32_t C, int32_t H, int32_t W, int32_t cpitch, void* stream);
+/* out[i] = sum_t in[t*n + i] for i < n (bf16 in, fp32 accumulation, bf16 out): gradient of the per-video skip term summed over the
+ * nt decoded frames of each video (autograd of the expand in srvp.py:222-223). n must be a multiple of 8. */
+int srvp_sum_over_time_bf16(const srvp_bf16* in, srvp_bf16* out, int32_t nt, int64_t n, void* stream);
 /* Materialises a fused source (BN apply, LeakyReLU, pool/upsample, frame gather) as dense NHWC bf16 (frames,H,W,channels). */
 int srvp_materialize_src(const srvp_conv_src* src, srvp_bf16* out, int32_t frames, int32_t H, int32_t W, void* stream);
 /* out[a][c][b] = in[a][b][c]; used to view 4x4 (de)conv weights as GEMM operands (module/conv.py:224, :330). */
@@ -183,7 +192,7 @@ typedef struct {
   int32_t lrelu;
   int32_t g_s2d;          /* apply: write dz as its space-to-depth image (frames,H/2,W/2,4C), channel (py*2+px)*C + c */
 } srvp_bn_bwd_args;
-int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t da_mode);
+int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t C, int32_t da_mode);
 int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* args, void* stream);
 int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,
                          void* stream);
@@ -230,6 +239,33 @@ typedef struct {
   int32_t split_k;     /* 0 = automatic (only splits accumulate-mode problems) */
 } srvp_gemm_args;
 int srvp_gemm(const srvp_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inference networks in fp32 on the CUDA cores (they feed the KL terms; < 0.1 % of the FLOPs): the small dense layers
+ * w_proj / w_inf / q_y / q_z (module/srvp.py:127-131, :133; called at :254-256, :275, :295) and the LSTM inf_z (:132, :365-368).
+ * srvp_linear_f32: C[m,n] (+)= act(sum_k A[m,k]*B[n,k] + bias[n] + bias2[n]), element strides, fixed summation order.
+ * srvp_act_bwd_f32: dx = dy * act'(y) from the activation OUTPUT y (ReLU / Tanh).
+ * srvp_lstm_fwd:   xproj (T,B,4H) = x W_ih^T + b_ih + b_hh (srvp_linear_f32), whh_t = W_hh^T (H,4H); zero initial state; gate order
+ *                  (i,f,g,o); outputs h_all, c_all (T,B,H) and the post-activation gates (T,B,4H) for the backward pass. One launch.
+ * srvp_lstm_bwd:   reverse-time pass: dgates (T,B,4H) = gradient w.r.t. the gate pre-activations, from dh_all (T,B,H), the saved
+ *                  gates / c_all and W_hh (4H,H). dW_ih, dW_hh, db, dx are then srvp_linear_f32 / srvp_colsum calls over T*B rows.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* a; int64_t a_sm, a_sk;
+  const float* b; int64_t b_sn, b_sk;
+  float* c; int64_t c_sm, c_sn;
+  const float* bias;   /* optional, indexed by n */
+  const float* bias2;  /* optional second bias (nn.LSTM has two) */
+  int32_t M, N, K;
+  int32_t act;         /* SRVP_ACT_* */
+  int32_t accumulate;  /* C += result (no activation) */
+} srvp_linear_args;
+int srvp_linear_f32(const srvp_linear_args* args, void* stream);
+int srvp_act_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, int32_t act, void* stream);
+int srvp_lstm_fwd(const float* xproj, const float* whh_t, float* h_all, float* c_all, float* gates, int32_t T, int32_t B, int32_t H,
+                  void* stream);
+int srvp_lstm_bwd(const float* dh_all, const float* gates, const float* c_all, const float* whh, float* dgates, int32_t T, int32_t B,
+                  int32_t H, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Latent residual dynamics: the Euler loop of generate() (module/srvp.py:325-413, _residual_step :300-323) as ONE

@@ -29,7 +29,8 @@ class Conv3x3Args(ctypes.Structure):
     _fields_ = [('src', ConvSrc * 2), ('nsrc', c_int), ('wpack', c_ptr), ('frames', c_int), ('H', c_int), ('W', c_int),
                 ('cout', c_int), ('cout_padded', c_int), ('epilogue', c_int), ('out', c_ptr), ('out_cpitch', c_int),
                 ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr), ('a_out', c_ptr), ('a_out_cpitch', c_int),
-                ('out_row_pitch', c_int), ('out_xstride', c_int), ('sigmoid_d2s', c_int), ('tap_mask', ctypes.c_uint16 * CONV_MAX_STAGES)]
+                ('out_row_pitch', c_int), ('out_xstride', c_int), ('sigmoid_d2s', c_int), ('tap_mask', ctypes.c_uint16 * CONV_MAX_STAGES),
+                ('add_f32', c_ptr), ('add_frames', c_int), ('out_raw_f32', c_ptr)]
 
 
 class Wgrad3x3Args(ctypes.Structure):
@@ -50,6 +51,12 @@ class GemmArgs(ctypes.Structure):
                 ('b_sn', c_i64), ('b_sk', c_i64), ('c', c_ptr), ('c_dtype', c_int), ('c_sm', c_i64), ('c_sn', c_i64),
                 ('bias', c_ptr), ('bias_on_m', c_int), ('M', c_int), ('N', c_int), ('K', c_int), ('act', c_int),
                 ('accumulate', c_int), ('split_k', c_int)]
+
+
+class LinearArgs(ctypes.Structure):
+    _fields_ = [('a', c_ptr), ('a_sm', c_i64), ('a_sk', c_i64), ('b', c_ptr), ('b_sn', c_i64), ('b_sk', c_i64), ('c', c_ptr),
+                ('c_sm', c_i64), ('c_sn', c_i64), ('bias', c_ptr), ('bias2', c_ptr), ('M', c_int), ('N', c_int), ('K', c_int),
+                ('act', c_int), ('accumulate', c_int)]
 
 
 MAX_MLP_LAYERS = 6
@@ -103,10 +110,11 @@ EXPORTS = [
     'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_launch_count', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
     'srvp_pack_conv3x3_weights', 'srvp_pack_conv4x4s2_weights', 'srvp_conv4x4s2_tap_mask', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16',
     'srvp_nchw_f32_to_s2d_bf16', 'srvp_sigmoid_bwd_nchw_to_s2d16', 'srvp_nhwc_bf16_to_nchw_f32',
-    'srvp_materialize_src', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
+    'srvp_materialize_src', 'srvp_sum_over_time_bf16', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
     'srvp_bn_tanh_rows_bwd_apply',
+    'srvp_linear_f32', 'srvp_act_bwd_f32', 'srvp_lstm_fwd', 'srvp_lstm_bwd',
     'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum',
 ]
 

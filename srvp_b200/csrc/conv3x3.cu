@@ -48,6 +48,9 @@ struct ConvDev {
   float* out_f32;
   __nv_bfloat16* a_out;  // optional copy of the transformed conv input (for the weight-gradient kernel)
   int a_out_cpitch;
+  const float* add;                // optional fp32 (add_frames, H, W, cout) tensor added to the accumulators of frame f % add_frames
+  int add_frames;
+  float* out_raw_f32;              // optional: the raw result is (also) stored as fp32 (F, H, W, cout)
   int out_row_pitch, out_xstride;  // output pixel index = (f*H + y)*out_row_pitch + x*out_xstride (dense: W, 1)
   int sig_d2s;                     // sigmoid epilogue: columns are (py,px,c) sub-pixel phases of a (F, cout/4, 2H, 2W) image
   int masked;                      // any K stage with fewer than nine taps (4x4 stride-2 family)
@@ -327,6 +330,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               const int bi = ps * BPP + bb;
               float vals[32];
               tmem_ld32(acc + mb * NB + bi * 32, vals);
+              if (p.add != nullptr && valid) {
+                // per-video term of a convolution split over cat[h, skip]: conv(cat[h, s]) = conv_h(h) + conv_s(s), s constant over time
+                const float4* ap = reinterpret_cast<const float4*>(p.add + ((size_t)(((f % p.add_frames) * p.H + y) * p.W + x)) * p.cout + nblk * NB + bi * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t4 = __ldg(ap + q);
+                  vals[4 * q] += t4.x; vals[4 * q + 1] += t4.y; vals[4 * q + 2] += t4.z; vals[4 * q + 3] += t4.w;
+                }
+              }
+              if (p.out_raw_f32 != nullptr && valid) {
+                float4* op = reinterpret_cast<float4*>(p.out_raw_f32 + ((size_t)((f * p.H + y) * p.W + x)) * p.cout + nblk * NB + bi * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) op[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+              }
               uint32_t pk[16];
 #pragma unroll
               for (int q = 0; q < 16; ++q) pk[q] = valid ? pack_bf16x2(vals[2 * q], vals[2 * q + 1]) : 0u;  // pad rows: zeros (never stored)
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
               const int r = r0 + lrow;
               const int pix = rowpix[r];
-              if (pix >= 0 && cbase < p.cout) {
+              if (pix >= 0 && cbase < p.cout && p.out != nullptr) {
                 const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
                 *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
               }
@@ -575,6 +592,12 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.out_f32 = a->out_f32_nchw;
   d.a_out = reinterpret_cast<__nv_bfloat16*>(a->a_out);
   d.a_out_cpitch = a->a_out_cpitch;
+  d.add = a->add_f32;
+  d.add_frames = a->add_frames;
+  d.out_raw_f32 = a->out_raw_f32;
+  if (a->add_f32 || a->out_raw_f32)
+    SRVP_REQUIRE(a->epilogue == SRVP_EPI_RAW_BF16 && a->cout % 64 == 0 && a->cout == a->cout_padded && (a->add_f32 == nullptr || a->add_frames > 0),
+                 "conv3x3: add / fp32 output need cout %% 64 == 0 (cout %d) and add_frames > 0", a->cout);
   d.out_row_pitch = a->out_row_pitch ? a->out_row_pitch : a->W;
   d.out_xstride = a->out_xstride ? a->out_xstride : 1;
   d.sig_d2s = a->sigmoid_d2s;
@@ -592,7 +615,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
     SRVP_REQUIRE(ch.NB == 16 && kper == 64 && a->out_f32_nchw != nullptr, "conv3x3: sigmoid epilogue needs cout<=16, 64-channel stages");
     return launch<16, 256, 8, 1, SRVP_EPI_SIGMOID_NCHW_F32>(d, stream, sms);
   }
-  SRVP_REQUIRE(a->out != nullptr && a->out_cpitch % 8 == 0 && a->out_coff % 8 == 0, "conv3x3: bad output tensor");
+  SRVP_REQUIRE((a->out != nullptr || a->out_raw_f32 != nullptr) && a->out_cpitch % 8 == 0 && a->out_coff % 8 == 0, "conv3x3: bad output tensor");
   if (kper == 16) {
     SRVP_REQUIRE(ch.NB == 64, "conv3x3: thin-input variant only built for 64 output channels");
     return launch<64, 512, 2, 9, SRVP_EPI_RAW_BF16>(d, stream, sms);

@@ -65,6 +65,23 @@ __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, f
   out[i] = __bfloat162float(in[(f * HW + p) * Cp + c]);
 }
 
+// out[i] = sum over t of in[t*n + i]; 8 elements per thread, fp32 accumulation.
+__global__ void sum_over_time_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int nt, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int t = 0; t < nt; ++t) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(in) + (long long)t * n8 + i);
+    const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
 // Materialises a fused source (BN apply + LeakyReLU + pool/upsample + frame gather) as NHWC bf16.
 __global__ void materialize_src_kernel(const SrcDev sd, __nv_bfloat16* __restrict__ out, long long total_chunks, int H, int W, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +214,7 @@ __device__ __forceinline__ void add_skip8(const BnBwdDev& p, int b, int y, int x
 //   reduce      s1 += g,  s2 += g * (z*is - mu_is)
 //   apply       dz = k0*g + z*ka + kb      with k0 = gamma*is, ka = -is*k0*c2, kb = k0*(mu*is*c2 - c1)
 template <int MODE, bool APPLY>
-__global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_kernel(const BnBwdDev p, long long items, int items_per_block, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_kernel(const BnBwdDev p, int items, int items_per_block, const float* __restrict__ gamma,
                                                        const float* __restrict__ c1, const float* __restrict__ c2) {
   __shared__ float red[APPLY ? 1 : 256 * 17];
   constexpr bool POOLED = MODE == SRVP_SRC_POOL2;
@@ -229,21 +246,23 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
   const int Hi = POOLED ? p.H / 2 : p.H, Wi = POOLED ? p.W / 2 : p.W;  // item grid
   const int Hd = UPS ? p.H * 2 : Hi, Wd = UPS ? p.W * 2 : Wi;          // da grid
-  const long long i0 = (long long)blockIdx.x * items_per_block;
-  const long long i1 = min(items, i0 + items_per_block);
-  for (long long itb = i0 + pl; itb < i1; itb += (long long)lanes * U) {
+  // 32-bit index arithmetic throughout (the host checks that the pixel count fits): 64-bit divisions per 16-byte chunk made this
+  // HBM-bound kernel instruction-bound
+  const int i0 = blockIdx.x * items_per_block;
+  const int i1 = min(items, i0 + items_per_block);
+  for (int itb = i0 + pl; itb < i1; itb += lanes * U) {
     uint4 dav[U][ND], zvv[U][NQ];
     int fy[U], yy[U], xx[U];
     bool act[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long it = itb + (long long)u * lanes;
+      const int it = itb + u * lanes;
       act[u] = it < i1;
-      const long long itc = act[u] ? it : i0;
-      xx[u] = (int)(itc % Wi);
-      const long long t2 = itc / Wi;
-      yy[u] = (int)(t2 % Hi);
-      fy[u] = (int)(t2 / Hi);
+      const unsigned itc = (unsigned)(act[u] ? it : i0);
+      const unsigned t2 = itc / (unsigned)Wi;
+      xx[u] = (int)(itc - t2 * (unsigned)Wi);
+      fy[u] = (int)(t2 / (unsigned)Hi);
+      yy[u] = (int)(t2 - (unsigned)fy[u] * (unsigned)Hi);
       const __nv_bfloat16* dbase = p.da + (((size_t)fy[u] * Hd + (UPS ? 2 * yy[u] : yy[u])) * Wd + (UPS ? 2 * xx[u] : xx[u])) * p.da_cpitch + p.da_coff + c0;
       dav[u][0] = __ldg(reinterpret_cast<const uint4*>(dbase));
       if (UPS) {
@@ -270,27 +289,31 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
 #pragma unroll
         for (int e = 0; e < 8; ++e) da[e] = (da[e] + t1[e]) + (t2[e] + t3[e]);
       }
-      float zv[NQ][8];
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) unpack8(zvv[u][q], zv[q]);
+      // the raw 16-byte chunks stay packed and are unpacked where they are used (4 x 8 floats at once would not fit the 128
+      // registers that two resident blocks per SM allow)
       int am[8];
       if (POOLED) {
+        float best[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float best = -INFINITY;
-          am[e] = 0;
+        for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; am[e] = 0; }
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) {
-            float v = fmaf(zv[q][e], sc[e], sh[e]);
+        for (int q = 0; q < NQ; ++q) {
+          float zq[8];
+          unpack8(zvv[u][q], zq);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = fmaf(zq[e], sc[e], sh[e]);
             if (p.lrelu) v = lrelu(v);
             v = bf16_round(v);  // the forward max-pool compared bf16-rounded activations; first maximum wins
-            if (v > best) { best = v; am[e] = q; }
+            if (v > best[e]) { best[e] = v; am[e] = q; }
           }
         }
       }
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int y = POOLED ? 2 * yi + (q >> 1) : yi, x = POOLED ? 2 * xi + (q & 1) : xi;
+        float zq[8];
+        unpack8(zvv[u][q], zq);
         float g[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) g[e] = POOLED ? (am[e] == q ? da[e] : 0.f) : da[e];
@@ -298,13 +321,13 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float pre = fmaf(zv[q][e], sc[e], sh[e]);
+          const float pre = fmaf(zq[e], sc[e], sh[e]);
           const float gg = g[e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
           if (APPLY) {
-            o[e] = fmaf(k0[e], gg, fmaf(zv[q][e], ka[e], kb[e]));
+            o[e] = fmaf(k0[e], gg, fmaf(zq[e], ka[e], kb[e]));
           } else {
             s1[e] += gg;
-            s2[e] = fmaf(gg, fmaf(zv[q][e], ka[e], -kb[e]), s2[e]);
+            s2[e] = fmaf(gg, fmaf(zq[e], ka[e], -kb[e]), s2[e]);
           }
         }
         if (APPLY) {
@@ -597,6 +620,14 @@ extern "C" int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32
   return check_launch("nhwc_to_nchw");
 }
 
+extern "C" int srvp_sum_over_time_bf16(const srvp_bf16* in, srvp_bf16* out, int32_t nt, int64_t n, void* stream) {
+  SRVP_REQUIRE(n % 8 == 0 && nt > 0, "sum_over_time: n=%lld must be a multiple of 8", (long long)n);
+  const long long n8 = n / 8;
+  sum_over_time_kernel<<<blocks_for(n8, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                            reinterpret_cast<__nv_bfloat16*>(out), nt, n8);
+  return check_launch("sum_over_time");
+}
+
 extern "C" int srvp_materialize_src(const srvp_conv_src* s, srvp_bf16* out, int32_t frames, int32_t H, int32_t W, void* stream) {
   SRVP_REQUIRE(s != nullptr && s->channels % 8 == 0, "materialize_src: bad source");
   SrcDev sd{reinterpret_cast<const __nv_bfloat16*>(s->ptr), s->scale, s->shift, s->frame_map, s->channels, s->cpitch, s->coff, s->mode, s->lrelu, s->row_pitch};
@@ -629,16 +660,22 @@ extern "C" int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, f
   return check_launch("channel_stats");
 }
 
-static int bn_bwd_blocks(long long items) {
-  long long nb = (items + 1023) / 1024;
+// Grid: enough blocks to fill the machine whatever the channel count (a block walks items_per_block pixels x C/8 chunks with 256
+// threads: ~8 loop iterations per thread), bounded by 8192 and by the size of the partial-sum buffer (blocks x C x 2 floats).
+static int bn_bwd_blocks(long long items, int C, int da_mode) {
+  const int U = (da_mode == SRVP_SRC_DIRECT) ? 4 : 2;
+  const long long chunk_items = items * (C / 8);
+  long long nb = (chunk_items + 256LL * U * 8 - 1) / (256LL * U * 8);
+  const long long cap = (1 << 20) / C;
+  if (nb > cap) nb = cap;
   if (nb > 8192) nb = 8192;
   if (nb < 1) nb = 1;
   return (int)nb;
 }
 
-extern "C" int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t da_mode) {
+extern "C" int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t C, int32_t da_mode) {
   const long long items = (da_mode == SRVP_SRC_POOL2) ? (long long)frames * (H / 2) * (W / 2) : (long long)frames * H * W;
-  return bn_bwd_blocks(items);
+  return bn_bwd_blocks(items, C, da_mode);
 }
 
 static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gamma, const float* c1, const float* c2, void* stream) {
@@ -661,12 +698,13 @@ static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gam
   const bool pooled = a->da_mode == SRVP_SRC_POOL2;
   if (pooled || a->da_mode == SRVP_SRC_UP2) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0 || !pooled, "bn_bwd: pooled mode needs even size");
   const long long items = pooled ? (long long)a->frames * (a->H / 2) * (a->W / 2) : (long long)a->frames * a->H * a->W;
-  const int nb = bn_bwd_blocks(items);
+  SRVP_REQUIRE(items * 4 < 2000000000LL, "bn_bwd: problem too large for 32-bit pixel indices");
+  const int nb = bn_bwd_blocks(items, a->C, a->da_mode);
   const int ipb = (int)((items + nb - 1) / nb);
   cudaStream_t st = (cudaStream_t)stream;
 #define SRVP_BN_LAUNCH(MODE)                                                                    \
-  if (apply) bn_bwd_kernel<MODE, true><<<nb, 256, 0, st>>>(d, items, ipb, gamma, c1, c2);       \
-  else bn_bwd_kernel<MODE, false><<<nb, 256, 0, st>>>(d, items, ipb, nullptr, nullptr, nullptr);
+  if (apply) bn_bwd_kernel<MODE, true><<<nb, 256, 0, st>>>(d, (int)items, ipb, gamma, c1, c2);       \
+  else bn_bwd_kernel<MODE, false><<<nb, 256, 0, st>>>(d, (int)items, ipb, nullptr, nullptr, nullptr);
   if (a->da_mode == SRVP_SRC_POOL2) { SRVP_BN_LAUNCH(SRVP_SRC_POOL2) }
   else if (a->da_mode == SRVP_SRC_UP2) { SRVP_BN_LAUNCH(SRVP_SRC_UP2) }
   else { SRVP_BN_LAUNCH(SRVP_SRC_DIRECT) }

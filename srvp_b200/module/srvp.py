@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import conv, utils
 from .mlp import MLP
-from .. import engine
+from .. import engine, infer
 
 
 class StochasticLatentResidualVideoPredictor(nn.Module):
@@ -117,21 +117,21 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
             h = hx[t.view(-1), index.view(-1)].view(self.nt_inf, bsz, self.nhx)
         else:
             h = hx[-self.nt_inf:]
-        return self.w_inf(self.w_proj(h).sum(0))
+        return infer.linear(infer.linear(h, self.w_proj[0], 'relu').sum(0), self.w_inf[0], 'tanh')
 
     def infer_y(self, hx):
         """module/srvp.py:258-278"""
-        q_y_0_params = self.q_y(hx.permute(1, 0, 2).reshape(hx.shape[1], self.nt_inf * self.nhx))
+        q_y_0_params = infer.mlp(hx.permute(1, 0, 2).reshape(hx.shape[1], self.nt_inf * self.nhx), self.q_y)
         return self._rsample(q_y_0_params), q_y_0_params
 
     def infer_z(self, hx):
         """module/srvp.py:280-298"""
-        q_z_params = self.q_z(hx)
+        q_z_params = infer.linear(hx, self.q_z)
         return self._rsample(q_z_params), q_z_params
 
     def _residual_step(self, y_t, z_tp1, dt):
         """module/srvp.py:300-323"""
-        res_tp1 = dt * self.dynamics(torch.cat([y_t, z_tp1], 1))
+        res_tp1 = dt * infer.mlp(torch.cat([y_t, z_tp1], 1), self.dynamics)
         return y_t + res_tp1, res_tp1
 
     def generate(self, y_0, hx, nt, dt, remove_intermediate=True):
@@ -146,11 +146,11 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
             assert not self.training                 # srvp.py:391
         q_z_params, z_post = None, None
         if n_obs > 0:
-            hx_z = self.inf_z(hx)[0]
+            hx_z = infer.lstm(hx, self.inf_z)                # one launch for the whole recurrence (srvp.py:365-368)
         # noise in the reference's order: one (B, nz) draw per generated frame (posterior or prior alike)
         eps = torch.stack([self._normal((bsz, self.nz), y_0) for _ in range(nt - 1)]) if nt > 1 else None
         if n_post > 0:
-            q_z_params = self.q_z(hx_z[1:n_post + 1])
+            q_z_params = infer.linear(hx_z[1:n_post + 1], self.q_z)
             loc, raw_scale = torch.chunk(q_z_params, 2, -1)
             z_post = loc + eps[:n_post] * (nn.functional.softplus(raw_scale) + 1e-8)
         y_all, p_z_params, z, res = latent.latent_loop(self.p_z, self.dynamics, y_0, z_post, eps, nt, oversampling, float(dt), n_post,

@@ -96,18 +96,28 @@ def padded_k(k):
 
 
 @profiled('pack_conv3x3')
-def pack_conv3x3(weight, kind, out=None):
-    """fp32 (.,.,3,3) weight -> packed bf16 B operand."""
+def pack_conv3x3(weight, kind, out=None, cin_range=None):
+    """fp32 (.,.,3,3) weight -> packed bf16 B operand. cin_range = (first, count) packs only those INPUT channels of an nn.Conv2d
+    weight ('conv': they are the K dimension; 'conv_dgrad': the N dimension) -- the two halves of a convolution over cat[h, skip]."""
     assert weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
     if kind in ('conv', 'conv_dgrad'):
         cout, cin = weight.shape[0], weight.shape[1]
     else:
         cin, cout = weight.shape[0], weight.shape[1]
     n_real, k_real, sn, sk, flip = conv3x3_kind_strides(kind, cout, cin)
+    wptr = ptr(weight)
+    if cin_range is not None:
+        assert kind in ('conv', 'conv_dgrad')
+        c0, cn = cin_range
+        wptr = ctypes.c_void_p(weight.data_ptr() + 4 * c0 * 9)
+        if kind == 'conv':
+            k_real = cn
+        else:
+            n_real = cn
     n_pad, k_pad = padded_n(n_real), padded_k(k_real)
     if out is None:
         out = torch.empty(n_pad * k_pad * 9, dtype=torch.bfloat16, device=weight.device)
-    check(lib().srvp_pack_conv3x3_weights(ptr(weight), ptr(out), c_int(n_real), c_int(n_pad), c_int(k_real), c_int(k_pad),
+    check(lib().srvp_pack_conv3x3_weights(wptr, ptr(out), c_int(n_real), c_int(n_pad), c_int(k_real), c_int(k_pad),
                                          c_i64(sn), c_i64(sk), c_int(flip), stream_ptr()), 'pack_conv3x3_weights')
     return out
 
@@ -148,7 +158,7 @@ def pack_conv4x4s2(weight, kind, chan_n, chan_k, stride_n, stride_k, py=0, px=0,
 
 @profiled('wgrad3x3')
 def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0, map4=0, phase_channels=0,
-             strides=None):
+             strides=None, dw_offset=0):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
 
     act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...)."""
@@ -160,7 +170,8 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
     a.dz_channels, a.dz_cpitch, a.dz_coff = dz_channels, dz.shape[-1], dz_coff
     a.frames, a.H, a.W = frames, H, W
     a.cout, a.cin = cout, cin
-    a.dw = ptr(dw)
+    assert dw.is_contiguous()
+    a.dw = ctypes.c_void_p(dw.data_ptr() + 4 * dw_offset)
     if strides is not None:          # 4x4 stride-2 family: (stride of the dz-side channel, stride of the act-side channel) in dw
         a.stride_cout, a.stride_cin, a.flip = strides[0], strides[1], 0
     elif kind == 'conv':
@@ -175,7 +186,8 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
 
 @profiled('conv3x3')
 def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None,
-            save_input=False, tap_masks=None, out_row_pitch=0, out_xstride=0, stats_out=None, a_out=None, sigmoid_d2s=False, taps=9):
+            save_input=False, tap_masks=None, out_row_pitch=0, out_xstride=0, stats_out=None, a_out=None, sigmoid_d2s=False, taps=9,
+            add=None, out_f32=False):
     """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None).
 
     4x4 stride-2 family (DCGAN64): tap_masks = one 9-bit mask per 64-channel K stage (or one int for all stages), out_row_pitch /
@@ -205,11 +217,19 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
         a.out_f32_nchw = ptr(out)
     else:
         a.epilogue = _lib.EPI_RAW_BF16
-        if out is None:
-            out = torch.empty(frames, H, W, cout, dtype=torch.bfloat16, device=dev)
-        a.out = ptr(out)
-        a.out_cpitch = out.shape[-1] if out_cpitch is None else out_cpitch
-        a.out_coff = out_coff
+        if add is not None:        # fp32 (add_frames, H, W, cout): per-video term added to the accumulators (frame f -> f % add_frames)
+            assert add.dtype == torch.float32 and tuple(add.shape[1:]) == (H, W, cout) and frames % add.shape[0] == 0
+            a.add_f32, a.add_frames = ptr(add), add.shape[0]
+        if out_f32:                # raw result kept in fp32 only (the per-video term itself)
+            out = torch.empty(frames, H, W, cout, dtype=torch.float32, device=dev)
+            a.out_raw_f32 = ptr(out)
+            a.out_cpitch = cout
+        else:
+            if out is None:
+                out = torch.empty(frames, H, W, cout, dtype=torch.bfloat16, device=dev)
+            a.out = ptr(out)
+            a.out_cpitch = out.shape[-1] if out_cpitch is None else out_cpitch
+            a.out_coff = out_coff
         if stats_out is not None:
             stats_partial = stats_out
             a.stats_partial = ptr(stats_partial)
@@ -262,6 +282,15 @@ def nhwc_to_nchw_f32(t, C):
     out = torch.empty(F_, C, H, W, dtype=torch.float32, device=t.device)
     check(lib().srvp_nhwc_bf16_to_nchw_f32(ptr(t), ptr(out), c_int(F_), c_int(C), c_int(H), c_int(W), c_int(cp), stream_ptr()),
           'nhwc_to_nchw')
+    return out
+
+
+@profiled('sum_over_time')
+def sum_over_time(t, nt):
+    """(nt*B, ...) bf16 -> (B, ...) bf16: sum over the nt leading blocks (fp32 accumulation)."""
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[0] % nt == 0
+    out = torch.empty(t.shape[0] // nt, *t.shape[1:], dtype=torch.bfloat16, device=t.device)
+    check(lib().srvp_sum_over_time_bf16(ptr(t), ptr(out), c_int(nt), c_i64(out.numel()), stream_ptr()), 'sum_over_time')
     return out
 
 
@@ -342,7 +371,7 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     (frames,H/2,W/2,4C) with g_s2d); accumulates dgamma/dbeta."""
     dev = z.device
     g = torch.empty((frames, H // 2, W // 2, 4 * C) if g_s2d else (frames, H, W, C), dtype=torch.bfloat16, device=dev)
-    rows = lib().srvp_bn_bwd_reduce_rows(c_int(frames), c_int(H), c_int(W), c_int(da_mode))
+    rows = lib().srvp_bn_bwd_reduce_rows(c_int(frames), c_int(H), c_int(W), c_int(C), c_int(da_mode))
     partial = torch.empty(rows, C, 2, dtype=torch.float32, device=dev)
     a = _lib.BnBwdArgs()
     a.z, a.scale, a.shift, a.mean, a.invstd = ptr(z), ptr(state.scale), ptr(state.shift), ptr(state.mean), ptr(state.invstd)

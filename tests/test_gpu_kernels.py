@@ -286,3 +286,51 @@ def test_layout_roundtrip_and_sigmoid_backward(dev):
     assert rel(dz[..., :3].float().permute(0, 3, 1, 2), dx * xh * (1 - xh)) < 5e-3
     t = torch.randn(7, 33, 65, device=dev)
     assert torch.equal(ops.transpose_last2(t), t.transpose(1, 2).contiguous())
+
+
+# ------------------------------------------------------------------------------------------------ fp32 inference networks
+@pytest.mark.parametrize('act', [None, 'relu', 'tanh'])
+def test_linear_f32_forward_backward(dev, act):
+    """srvp_linear_f32 + srvp_act_bwd_f32 + srvp_colsum against nn.Linear autograd (fp32, matmul TF32 off): 1e-5 relative."""
+    from srvp_b200 import infer
+    lin = torch.nn.Linear(130, 77).to(dev)
+    x = torch.randn(3, 67, 130, device=dev, requires_grad=True)
+    y = infer.linear(x, lin, act)
+    x2 = x.detach().clone().requires_grad_(True)
+    lin2 = torch.nn.Linear(130, 77).to(dev)
+    lin2.load_state_dict(lin.state_dict())
+    y2 = lin2(x2)
+    y2 = torch.relu(y2) if act == 'relu' else torch.tanh(y2) if act == 'tanh' else y2
+    assert rel(y, y2) < 1e-5
+    g = torch.randn_like(y)
+    y.backward(g)
+    y2.backward(g)
+    assert rel(x.grad, x2.grad) < 1e-5 and rel(lin.weight.grad, lin2.weight.grad) < 1e-5 and rel(lin.bias.grad, lin2.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize('T,B', [(12, 192), (5, 3), (1, 7)])
+def test_lstm_forward_backward(dev, T, B):
+    """One-launch LSTM recurrence and its reverse-time pass against nn.LSTM (cuDNN, TF32 disabled): 2e-5 relative."""
+    from srvp_b200 import infer
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.LSTM(128, 256, 1).to(dev)
+        ours = torch.nn.LSTM(128, 256, 1).to(dev)
+        ours.load_state_dict(ref.state_dict())
+        x = torch.randn(T, B, 128, device=dev, requires_grad=True)
+        x2 = x.detach().clone().requires_grad_(True)
+        h = infer.lstm(x, ours)
+        h2 = ref(x2)[0]
+        assert rel(h, h2) < 2e-5
+        g = torch.randn_like(h)
+        h.backward(g)
+        h2.backward(g)
+        assert rel(x.grad, x2.grad) < 2e-5
+        for n in ['weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0']:
+            if T == 1 and n == 'weight_hh_l0':
+                assert float(getattr(ours, n).grad.abs().max()) == 0.0
+                continue
+            assert rel(getattr(ours, n).grad, getattr(ref, n).grad) < 2e-5, n
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32

@@ -28,15 +28,15 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors must have the C layout (checked against a tiny C program compiled with gcc)."""
     from srvp_b200 import _lib
-    src = '#include <stdio.h>\n#include "srvp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(srvp_conv_src), ' \
+    src = '#include <stdio.h>\n#include "srvp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(srvp_conv_src), ' \
           'sizeof(srvp_conv3x3_args), sizeof(srvp_wgrad3x3_args), sizeof(srvp_bn_bwd_args), sizeof(srvp_gemm_args), ' \
-          'sizeof(srvp_latent_fwd_args), sizeof(srvp_latent_bwd_args));return 0;}\n'
+          'sizeof(srvp_latent_fwd_args), sizeof(srvp_latent_bwd_args), sizeof(srvp_linear_args));return 0;}\n'
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, 't.c'), 'w').write(src)
         subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')], check=True)
         sizes = [int(v) for v in subprocess.run([os.path.join(d, 't')], capture_output=True, text=True, check=True).stdout.split()]
-    mirrors = [_lib.ConvSrc, _lib.Conv3x3Args, _lib.Wgrad3x3Args, _lib.BnBwdArgs, _lib.GemmArgs, _lib.LatentFwdArgs, _lib.LatentBwdArgs]
+    mirrors = [_lib.ConvSrc, _lib.Conv3x3Args, _lib.Wgrad3x3Args, _lib.BnBwdArgs, _lib.GemmArgs, _lib.LatentFwdArgs, _lib.LatentBwdArgs, _lib.LinearArgs]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
