@@ -83,15 +83,9 @@ class ClockSampler(threading.Thread):
 
 
 def elbo_loss(out, x):
-    import torch.distributions as distrib
-    from srvp_b200.module import utils
-    x_, y, z, _, q_y_0_params, q_z_params, p_z_params, res = out
-    n = x.shape[1]
-    nll = utils.neg_logprob(x_, x, scale=LOSS['obs_scale']).sum()
-    kl_y_0 = distrib.kl_divergence(utils.make_normal_from_raw_params(q_y_0_params), distrib.Normal(0, 1)).sum()
-    kl_z = distrib.kl_divergence(utils.make_normal_from_raw_params(q_z_params), utils.make_normal_from_raw_params(p_z_params)).sum()
-    loss = nll + LOSS['beta_y'] * kl_y_0 + LOSS['beta_z'] * kl_z + LOSS['l2_res'] * torch.norm(res, p=2, dim=2).sum()
-    return loss / n
+    """train.py:90-106 through the fused ELBO reductions (srvp_b200/elbo.py)."""
+    from srvp_b200 import elbo
+    return elbo.elbo(out, x, LOSS['obs_scale'], LOSS['beta_y'], LOSS['beta_z'], LOSS['l2_res'])[0]
 
 
 def run_ours(args):
@@ -190,8 +184,12 @@ def run_ours(args):
     roofline = dict(bound='tensor', kernel=dom, achieved=round(achieved, 1), peak=pk['tf'], unit='TFLOP/s', frac=round(achieved / pk['tf'], 4),
                     traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)', share_of_kernel_time=round(d['ms'] / tot_ms, 3),
                     launches_per_step=d['launches'] // 2, avg_launch_ms=round(d['ms'] / d['launches'], 4))
+    roofline['executed'] = round(d['executed_flops'] / (d['ms'] * 1e-3) / 1e12, 1)
+    roofline['note'] = ('achieved = dense FLOPs of the reference ops these launches stand for (SURVEY.md 8d) / time; executed = multiply-adds '
+                        'actually issued (the convolutions over cat[h, skip] are split per video, DESIGN.md section 4)')
     breakdown = {k: dict(ms_per_step=round(v['ms'] / 2, 3), launches=v['launches'] // 2,
                          tflops=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['flops'] else None,
+                         executed_tflops=round(v['executed_flops'] / (v['ms'] * 1e-3) / 1e12, 1) if v['executed_flops'] else None,
                          gbs=round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1) if v['bytes'] else None) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
     if world > 1:
         dist.barrier()

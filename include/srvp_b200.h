@@ -268,6 +268,24 @@ int srvp_lstm_bwd(const float* dh_all, const float* gates, const float* c_all, c
                   int32_t H, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ELBO terms (loss assembly of train.py:90-106 over module/utils.py:88-112, :137-159) as fused reductions.
+ * `partial` is a scratch buffer of SRVP_ELBO_MAX_PARTIALS floats; `out` a device scalar. Sums are deterministic (fixed order, fp64 over
+ * blocks). The KL / L2 calls also write the gradient w.r.t. their inputs for an upstream gradient of 1; backward scales it
+ * (srvp_scale_by_scalar_f32, upstream gradient read from device memory: no host synchronisation anywhere).
+ *   srvp_nll_fwd       out = sum (x - xhat)^2 / (2 s^2) + n (log s + 1/2 log 2 pi)              utils.neg_logprob(x_, x, s).sum()
+ *   srvp_nll_bwd       dxhat = g[0] * (xhat - x) / s^2
+ *   srvp_kl_normal_fwd out = sum KL(N(mu_q, softplus(rho_q)+1e-8) || N(mu_p, softplus(rho_p)+1e-8)); q, p: (rows, 2d) raw parameters
+ *                      (mu | rho) as utils.make_normal_from_raw_params splits them; p = NULL: standard normal prior (train.py:95)
+ *   srvp_l2_rows_fwd   out = sum over rows of ||res[row, :]||_2 (train.py:103), dres = res / ||res||
+ * ---------------------------------------------------------------------------------------------- */
+enum { SRVP_ELBO_MAX_PARTIALS = 2048 };
+int srvp_nll_fwd(const float* xhat, const float* x, int64_t n, float obs_scale, float* partial, float* out, void* stream);
+int srvp_nll_bwd(const float* xhat, const float* x, int64_t n, float obs_scale, const float* g, float* dxhat, void* stream);
+int srvp_kl_normal_fwd(const float* q, const float* p, int64_t rows, int32_t d, float* partial, float* out, float* dq, float* dp, void* stream);
+int srvp_l2_rows_fwd(const float* res, int64_t rows, int32_t d, float* partial, float* out, float* dres, void* stream);
+int srvp_scale_by_scalar_f32(const float* in, const float* g, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Latent residual dynamics: the Euler loop of generate() (module/srvp.py:325-413, _residual_step :300-323) as ONE
  * persistent launch. p_z = MLP(ny -> nh ... -> 2nz), dynamics = MLP(ny+nz -> nh ... -> ny) (module/mlp.py:47-90):
  *   every Euler step s (os sub-steps per frame): first sub-step of frame f: p_z(y) -> pz_out[f]; z[f] = z_post[f] for

@@ -85,6 +85,7 @@ ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 SRC_DIRECT, SRC_POOL2, SRC_UP2 = 0, 1, 2
 EPI_RAW_BF16, EPI_SIGMOID_NCHW_F32 = 0, 1
 W4_DOWN, W4_UP_PHASE, W4_UP_ALL = 1, 2, 3
+ELBO_MAX_PARTIALS = 2048
 
 _lib = None
 
@@ -114,6 +115,7 @@ EXPORTS = [
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
     'srvp_bn_tanh_rows_bwd_apply',
+    'srvp_nll_fwd', 'srvp_nll_bwd', 'srvp_kl_normal_fwd', 'srvp_l2_rows_fwd', 'srvp_scale_by_scalar_f32',
     'srvp_linear_f32', 'srvp_act_bwd_f32', 'srvp_lstm_fwd', 'srvp_lstm_bwd',
     'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum',
 ]

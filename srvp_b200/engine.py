@@ -256,7 +256,7 @@ def _skip_src(level, frame_map):
     return Src(level, level.shape[-1], None, None, frame_map, 0, SRC_DIRECT, False)  # already-activated NHWC bf16 tensor
 
 
-def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, want_stats_update=True):
+def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, want_stats_update=True, sel=None):
     """dec_inp: (F, ny_in) fp32. skip_levels: deepest-first list of fused levels or NHWC bf16 tensors. Returns (x_hat NCHW fp32, ctx)."""
     plan = _ensure_plan(dec)
     assert sigmoid, 'srvp_b200: decoder without the final sigmoid is not built'
@@ -282,13 +282,32 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
         if training and want_stats_update:
             torch._foreach_add_([b.num_batches_tracked for b in _bn_list(dec)], 1)
         return c.x_hat, c
+    # Convolutions over cat[h, skip] (conv.py:270) are split: conv(cat[h, s]) = conv_h(h) + conv_s(s). The skip features are those of
+    # ONE frame per video, repeated over the nt decoded frames (srvp.py:222-223), so conv_s runs over B frames instead of nt*B and its
+    # fp32 result is added to the accumulators of the per-frame launch (same sums, different order; 1/2 * 11/12 of these layers' MMAs
+    # disappear in forward, data gradient and weight gradient alike). Needs the per-video structure: `sel` = encoder frame per video.
+    c.split = {}
+    c.skip_c0 = {}
     for blk in plan:
-        srcs = [Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, blk.in_mode, True)]
-        if blk.skip_level is not None:
-            srcs.append(_skip_src(skip_levels[blk.skip_level], frame_map))
-        wp = ops.pack_conv3x3(blk.conv.weight, 'conv')
+        li = len(c.z)
+        h_src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, blk.in_mode, True)
         st = BNState(blk.cout, dev)
-        r = ops.conv3x3(srcs, wp, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training)
+        c.skip_c0[li] = h_src.channels
+        if blk.skip_level is not None and sel is not None and F_ % sel.shape[0] == 0 and blk.cout % 64 == 0:
+            nvid = sel.shape[0]
+            s_src = _skip_src(skip_levels[blk.skip_level], sel)
+            wp_s = ops.pack_conv3x3(blk.conv.weight, 'conv', cin_range=(h_src.channels, s_src.channels))
+            rs = ops.conv3x3([s_src], wp_s, nvid, blk.res, blk.res, blk.cout, out_f32=True, save_input=training, alg_scale=0.0)
+            wp_h = ops.pack_conv3x3(blk.conv.weight, 'conv', cin_range=(0, h_src.channels))
+            r = ops.conv3x3([h_src], wp_h, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training, add=rs[0],
+                            alg_scale=(h_src.channels + s_src.channels) / h_src.channels)
+            c.split[li] = (rs[2] if training else None, s_src.channels, nvid)
+        else:
+            srcs = [h_src]
+            if blk.skip_level is not None:
+                srcs.append(_skip_src(skip_levels[blk.skip_level], frame_map))
+            wp = ops.pack_conv3x3(blk.conv.weight, 'conv')
+            r = ops.conv3x3(srcs, wp, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training)
         z, partial = r[0], r[1]
         if training:
             ops.bn_finalize(partial, float(F_ * blk.res * blk.res), blk.bn, st, training_update=want_stats_update)
@@ -297,8 +316,6 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
         c.z.append(z)
         c.st.append(st)
         c.srcs.append(r[2] if training else None)
-        c.skip_c0 = getattr(c, 'skip_c0', {})
-        c.skip_c0[len(c.z) - 1] = srcs[0].channels
         prev = Src(z, blk.cout, st.scale, st.shift, None, 0, SRC_DIRECT, True)
     final = dec.conv[3][1]
     c.final_src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, SRC_DIRECT, True)
@@ -333,13 +350,29 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
         gi = 3 + 3 * li
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[gi + 1], grads[gi + 2], da, da_mode, F_, blk.res, blk.res, blk.cout,
                         da_coff=da_coff, sync=ops.is_sync_bn(blk.bn))
-        cin_tot = c.srcs[li].shape[-1]
-        ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv')
-        wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
-        da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, cin_tot)
+        if li in c.split:
+            # split layer: h half over all frames, skip half over the per-video sums of dz (weight (cout, ch + cs, 3, 3))
+            a_s, cs, nvid = c.split[li]
+            ch = c.srcs[li].shape[-1]
+            cin_tot = ch + cs
+            ops.wgrad3x3(c.srcs[li], ch, dz, blk.cout, F_, blk.res, blk.res, blk.cout, ch, grads[gi], 'conv', strides=(cin_tot * 9, 9),
+                         alg_scale=cin_tot / ch)
+            dzs = ops.sum_over_time(dz, F_ // nvid)
+            ops.wgrad3x3(a_s, cs, dzs, blk.cout, nvid, blk.res, blk.res, blk.cout, cs, grads[gi], 'conv', strides=(cin_tot * 9, 9), dw_offset=ch * 9,
+                         alg_scale=0.0)
+            wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad', cin_range=(0, ch))
+            da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, ch, alg_scale=cin_tot / ch)
+            wp_s = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad', cin_range=(ch, cs))
+            d_skip, _ = ops.conv3x3([Src(dzs, blk.cout)], wp_s, nvid, blk.res, blk.res, cs, alg_scale=0.0)
+            skip_grads[blk.skip_level] = (d_skip, 0)       # already summed over time: the encoder sees nt = 1
+        else:
+            cin_tot = c.srcs[li].shape[-1]
+            ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv')
+            wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
+            da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, cin_tot)
+            if blk.skip_level is not None:
+                skip_grads[blk.skip_level] = (da, c.skip_c0[li])
         da_mode, da_coff = blk.in_mode, 0
-        if blk.skip_level is not None:
-            skip_grads[blk.skip_level] = (da, c.skip_c0[li])
     if skip_handle is not None and skip_grads:
         skip_handle.grads = [skip_grads[i] for i in range(len(skip_grads))]
     return _decoder_head_bwd(dec, c, da, SRC_UP2, grads)
@@ -361,8 +394,8 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads):
 
 class DecoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dec, dec_inp, skip_levels, frame_map, skip_handle, *params):
-        x_hat, c = _decoder_fwd(dec, dec_inp.contiguous(), skip_levels, frame_map, dec.training)
+    def forward(ctx, dec, dec_inp, skip_levels, frame_map, skip_handle, sel, *params):
+        x_hat, c = _decoder_fwd(dec, dec_inp.contiguous(), skip_levels, frame_map, dec.training, sel=sel)
         ctx.dec, ctx.c, ctx.skip_handle = dec, c, skip_handle
         return x_hat
 
@@ -370,12 +403,14 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, d_xhat):
         d_inp, grads = _decoder_bwd(ctx.dec, ctx.c, d_xhat, ctx.skip_handle)
         ctx.c = None
-        return (None, d_inp, None, None, None, *grads)
+        return (None, d_inp, None, None, None, None, *grads)
 
 
-def decoder_apply(dec, dec_inp, skip_levels, frame_map, skip_handle):
+def decoder_apply(dec, dec_inp, skip_levels, frame_map, skip_handle, sel=None):
+    """sel (B,) int32: encoder frame feeding each video's skip connection, when the decoder frames are (t, b)-ordered with
+    frame_map = sel.repeat(nt); it enables the per-video split of the convolutions over cat[h, skip]."""
     _ensure_plan(dec)
-    return DecoderFn.apply(dec, dec_inp, skip_levels, frame_map, skip_handle, *_dec_params(dec))
+    return DecoderFn.apply(dec, dec_inp, skip_levels, frame_map, skip_handle, sel, *_dec_params(dec))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -47,9 +47,15 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         self.dynamics.apply(lambda m: utils.init_weight(m, init_type='orthogonal', init_gain=res_gain))
 
     # ------------------------------------------------------------------------------------------------ noise
+    @staticmethod
+    def _to_device(t, device):
+        """Host tensor -> device without stalling the host: a pageable-memory copy waits for the stream to drain (a hidden host
+        synchronisation per call); staging through the caching pinned allocator keeps it asynchronous and stream-safe."""
+        return t.pin_memory().to(device, non_blocking=True)
+
     def _normal(self, shape, like):
         if self.noise_device == 'cpu':
-            return torch.empty(shape, dtype=torch.float32).normal_().to(like.device, non_blocking=True)
+            return self._to_device(torch.empty(shape, dtype=torch.float32).normal_(), like.device)
         return torch.empty(shape, dtype=torch.float32, device=like.device).normal_()
 
     def _rsample(self, raw_params):
@@ -72,8 +78,8 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
             inv = torch.full((nt * bsz,), -1, dtype=torch.int32)
             inv[sel.long()] = torch.arange(bsz, dtype=torch.int32)
             handle.T, handle.B = nt, bsz
-            handle.frame_map = sel.to(x.device, non_blocking=True)        # (B,), expanded per decode call
-            handle.inv_map = inv.to(x.device, non_blocking=True)
+            handle.frame_map = self._to_device(sel, x.device)             # (B,), expanded per decode call
+            handle.inv_map = self._to_device(inv, x.device)
         return hx, handle
 
     def encode(self, x):
@@ -94,7 +100,7 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         frame_map = None
         if levels is not None:
             frame_map = sel.repeat(nt)                                    # decoder frame (t, b) -> source frame of video b
-        x_flat = engine.decoder_apply(self.decoder, dec_inp, levels, frame_map, handle)
+        x_flat = engine.decoder_apply(self.decoder, dec_inp, levels, frame_map, handle, sel=sel)
         return x_flat.view(nt, bsz, *x_flat.shape[1:])
 
     def decode(self, w, y, skip):
@@ -112,7 +118,7 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         """module/srvp.py:229-256"""
         nt, bsz = hx.shape[0], hx.shape[1]
         if self.training:
-            t = torch.stack([torch.randperm(nt)[:self.nt_inf] for _ in range(bsz)], 1).to(hx.device)
+            t = self._to_device(torch.stack([torch.randperm(nt)[:self.nt_inf] for _ in range(bsz)], 1), hx.device)
             index = torch.arange(bsz, device=hx.device).repeat(self.nt_inf, 1)
             h = hx[t.view(-1), index.view(-1)].view(self.nt_inf, bsz, self.nhx)
         else:

@@ -22,11 +22,11 @@ def profiled(name):
                 return fn(*args, **kwargs)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _WORK.append([0.0, 0.0])
+            _WORK.append([0.0, 0.0, 0.0])
             out = fn(*args, **kwargs)
             e1.record()
-            fl, by = _WORK.pop()
-            PROFILE.setdefault(name, []).append((e0, e1, fl, by))
+            fl, by, fx = _WORK.pop()
+            PROFILE.setdefault(name, []).append((e0, e1, fl, by, fx))
             return out
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__
@@ -37,18 +37,22 @@ def profiled(name):
 _WORK = []
 
 
-def _account(flops=0.0, nbytes=0.0):
+def _account(flops=0.0, nbytes=0.0, executed=None):
+    """flops: ALGORITHMIC dense count of the reference op this launch stands for; executed: multiply-adds actually
+    issued when they differ (per-video split of the skip convolutions)."""
     if _WORK:
         _WORK[-1][0] += flops
         _WORK[-1][1] += nbytes
+        _WORK[-1][2] += flops if executed is None else executed
 
 
 def summarize_profile(profile):
     """{name: dict(launches, ms, flops, bytes)} -- call after torch.cuda.synchronize()."""
     out = {}
     for name, recs in profile.items():
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs)
-        out[name] = dict(launches=len(recs), ms=ms, flops=sum(r[2] for r in recs), bytes=sum(r[3] for r in recs))
+        ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+        out[name] = dict(launches=len(recs), ms=ms, flops=sum(r[2] for r in recs), bytes=sum(r[3] for r in recs),
+                         executed_flops=sum(r[4] for r in recs))
     return out
 
 
@@ -158,7 +162,7 @@ def pack_conv4x4s2(weight, kind, chan_n, chan_k, stride_n, stride_k, py=0, px=0,
 
 @profiled('wgrad3x3')
 def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0, map4=0, phase_channels=0,
-             strides=None, dw_offset=0):
+             strides=None, dw_offset=0, alg_scale=1.0):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
 
     act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...)."""
@@ -180,14 +184,15 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
         a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
     a.map4, a.phase_channels = map4, phase_channels
     check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
-    _account(2.0 * frames * H * W * cout * cin * (4 if map4 else 9), 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel())
+    fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
+    _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx)
     return dw
 
 
 @profiled('conv3x3')
 def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None,
             save_input=False, tap_masks=None, out_row_pitch=0, out_xstride=0, stats_out=None, a_out=None, sigmoid_d2s=False, taps=9,
-            add=None, out_f32=False):
+            add=None, out_f32=False, alg_scale=1.0):
     """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None).
 
     4x4 stride-2 family (DCGAN64): tap_masks = one 9-bit mask per 64-channel K stage (or one int for all stages), out_row_pitch /
@@ -244,7 +249,9 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
     cin_real = cin_real if cin_real is not None else sum(s.channels for s in srcs)
     obytes = (out.numel() * out.element_size()) if not out_xstride else 2.0 * frames * H * W * cout
-    _account(2.0 * frames * H * W * cout * cin_real * taps, sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
+    fx = 2.0 * frames * H * W * cout * cin_real * taps
+    # alg_scale: algorithmic (reference, dense) FLOPs this launch stands for / executed ones (split skip convolutions: 2 and 0)
+    _account(fx * alg_scale, executed=fx, nbytes= sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
     if save_input:
         return out, stats_partial, a_out
     return out, stats_partial

@@ -334,3 +334,32 @@ def test_lstm_forward_backward(dev, T, B):
             assert rel(getattr(ours, n).grad, getattr(ref, n).grad) < 2e-5, n
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+
+
+# ------------------------------------------------------------------------------------------------ fused ELBO reductions
+def test_fused_elbo_matches_torch_distributions(dev):
+    """srvp_b200.elbo.elbo against the reference's loss assembly (train.py:90-106 via module/utils.py): values 1e-6, gradients 1e-5."""
+    from common import model_loss
+    from srvp_b200 import elbo
+    T, B, ny, nz, S = 5, 7, 20, 30, 8
+    g = torch.Generator(device='cpu').manual_seed(4)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev).requires_grad_(True)
+    x = torch.rand(T, B, 3, 64, 64, generator=g).to(dev)
+    x_ = torch.rand(T, B, 3, 64, 64, generator=g).to(dev).requires_grad_(True)
+    qy, qz, pz, res = mk(B, 2 * ny), mk(T - 1, B, 2 * nz), mk(T - 1, B, 2 * nz), mk(S, B, ny)
+    with torch.no_grad():
+        qz[0, 0, nz:] = 25.0      # softplus threshold branch
+        res[0, 0] = 0.0           # zero residual row: norm gradient 0
+    loss_cfg = dict(obs_scale=0.71, beta_y=1.5, beta_z=2.0, l2_res=0.7)
+    out = (x_, None, None, None, qy, qz, pz, res)
+    l1, n1, ky1, kz1 = elbo.elbo(out, x, **loss_cfg)
+    l1.backward()
+    g1 = [t.grad.clone() for t in (x_, qy, qz, pz, res)]
+    for t in (x_, qy, qz, pz, res):
+        t.grad = None
+    l2, n2, ky2, kz2 = model_loss(out, x, loss_cfg)
+    l2.backward()
+    for a, b in [(l1, l2), (n1, n2), (ky1, ky2), (kz1, kz2)]:
+        assert float(a) == pytest.approx(float(b), rel=2e-6)
+    for a, t in zip(g1, (x_, qy, qz, pz, res)):
+        assert rel(a, t.grad) < 1e-5

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.distributions as distrib
 
+from srvp_b200 import elbo
 from srvp_b200.module import srvp, utils
 
 
@@ -27,15 +28,10 @@ def train(forward_fn, optimizer, scaler, batch, device, opt):
     x = batch.to(device)
     nt, n = x.shape[0], x.shape[1]
     x_, y, z, _, q_y_0_params, q_z_params, p_z_params, res = forward_fn(x, nt, dt=1 / opt.n_euler_steps)
-    nll = utils.neg_logprob(x_, x, scale=opt.obs_scale).sum()
-    q_y_0 = utils.make_normal_from_raw_params(q_y_0_params)
-    kl_y_0 = distrib.kl_divergence(q_y_0, distrib.Normal(0, 1)).sum()
-    q_z, p_z = utils.make_normal_from_raw_params(q_z_params), utils.make_normal_from_raw_params(p_z_params)
-    kl_z = distrib.kl_divergence(q_z, p_z).sum()
-    loss = nll + opt.beta_y * kl_y_0 + opt.beta_z * kl_z
-    if opt.l2_res > 0:
-        loss = loss + opt.l2_res * torch.norm(res, p=2, dim=2).sum()
-    loss = loss / n
+    # ELBO of train.py:90-106 as fused reductions (srvp_b200/elbo.py); utils.neg_logprob / make_normal_from_raw_params remain for
+    # code written against the reference
+    loss, nll, kl_y_0, kl_z = elbo.elbo((x_, y, z, _, q_y_0_params, q_z_params, p_z_params, res), x, opt.obs_scale, opt.beta_y, opt.beta_z,
+                                        opt.l2_res)
     loss.backward()
     optimizer.step()
     with torch.no_grad():
