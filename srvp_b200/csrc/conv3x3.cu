@@ -145,59 +145,136 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         const int cloc = cb * KCH * 8;  // first channel of this stage within the source's consumed range
         mbar_wait(&halo_empty[hs], ((it / kHaloStages) & 1) ^ 1);
         uint8_t* hbuf = halo + (size_t)hs * KCH * P * 16;
-        for (int r = lt; r < P; r += kLoaders) {
-          const long long vin = vbase + r;
-          bool valid = vin >= 0 && vin < p.vtotal;
-          int f = 0, y = 0, x = 0;
-          if (valid) {
-            f = (int)(vin / HpWp);
-            const int rem = (int)(vin - (long long)f * HpWp);
-            y = rem / p.Wp;
-            x = rem - y * p.Wp;
-            valid = (y < p.H) && (x < p.W);
-          }
-          if (!valid) {
+        if (sd.mode != SRVP_SRC_POOL2) {
+          // One-to-one sources (DIRECT / UP2): every row this thread owns is fetched with asynchronous 16-byte copies straight into
+          // its place in the halo tile (all of them in flight at once, zero-filled for pad pixels), then transformed in place
+          // (BN scale/shift + LeakyReLU) once they have landed. The register-staged version exposed one DRAM latency per row.
+          constexpr int MAXR = 3;   // rows per thread: P <= MAXR * kLoaders (checked on the host)
+          const int rp = sd.row_pitch ? sd.row_pitch : p.W;
+          int pix[MAXR];            // output pixel index of a valid row (for a_out), -1 = pad row
 #pragma unroll
-            for (int j = 0; j < KCH; ++j) *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = make_uint4(0, 0, 0, 0);
-            continue;
+          for (int k = 0; k < MAXR; ++k) {
+            const int r = lt + k * kLoaders;
+            pix[k] = -1;
+            if (r < P) {
+              const long long vin = vbase + r;
+              bool valid = vin >= 0 && vin < p.vtotal;
+              int f = 0, y = 0, x = 0;
+              if (valid) {
+                const unsigned v = (unsigned)vin;
+                f = (int)(v / (unsigned)HpWp);
+                const unsigned rem = v - (unsigned)f * (unsigned)HpWp;
+                y = (int)(rem / (unsigned)p.Wp);
+                x = (int)(rem - (unsigned)y * (unsigned)p.Wp);
+                valid = (y < p.H) && (x < p.W);
+              }
+              const __nv_bfloat16* src = sd.ptr;
+              if (valid) {
+                const int fs = sd.frame_map ? __ldg(sd.frame_map + f) : f;
+                if (sd.mode == SRVP_SRC_UP2) src = sd.ptr + (((size_t)fs * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * sd.cpitch + sd.coff + cloc;
+                else src = sd.ptr + (((size_t)fs * p.H + y) * rp + x) * sd.cpitch + sd.coff + cloc;
+                pix[k] = (f * p.H + y) * p.W + x;
+              }
+              const uint32_t nbytes = valid ? 16u : 0u;
+              const int step = valid ? 8 : 0;
+#pragma unroll
+              for (int j = 0; j < KCH; ++j) cp_async16(hbuf + ((size_t)j * P + r) * 16, src + j * step, nbytes);
+            }
           }
-          const int fs = sd.frame_map ? __ldg(sd.frame_map + f) : f;
+          cp_async_wait_all();
           const float* sc = sd.scale ? sd.scale + cloc : nullptr;
           const float* sh = sd.shift ? sd.shift + cloc : nullptr;
-          if (sd.mode == SRVP_SRC_POOL2) {
-            const int Ws = p.W * 2;
-            const __nv_bfloat16* base = sd.ptr + (((size_t)fs * (p.H * 2) + 2 * y) * Ws + 2 * x) * sd.cpitch + sd.coff + cloc;
+          if (sc != nullptr || sd.lrelu || store_a) {
+            if constexpr (MT >= 512) {
+              // 2-3 rows per thread: chunk-major, the 8 channels' scale / shift are loaded once and reused over this thread's rows
+#pragma unroll 2
+              for (int j = 0; j < KCH; ++j) {
+                const Affine8 af = load_affine8(sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr);
 #pragma unroll
-            for (int j = 0; j < KCH; ++j) {
-              const uint4 r00 = __ldg(reinterpret_cast<const uint4*>(base + j * 8));
-              const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(base + sd.cpitch + j * 8));
-              const uint4 r10 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * sd.cpitch + j * 8));
-              const uint4 r11 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(Ws + 1) * sd.cpitch + j * 8));
-              const float* scj = sc ? sc + j * 8 : nullptr;
-              const float* shj = sh ? sh + j * 8 : nullptr;
-              uint4 a = max8(max8(transform8(r00, scj, shj, sd.lrelu), transform8(r01, scj, shj, sd.lrelu)),
-                             max8(transform8(r10, scj, shj, sd.lrelu), transform8(r11, scj, shj, sd.lrelu)));
+                for (int k = 0; k < MAXR; ++k) {
+                  const int r = lt + k * kLoaders;
+                  if (pix[k] < 0) continue;   // pad rows stay zero
+                  uint4* slot = reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16);
+                  const uint4 a = transform8r(*slot, af, sd.lrelu);
+                  if (af.on || sd.lrelu) *slot = a;
+                  if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
+                    *reinterpret_cast<uint4*>(p.a_out + (size_t)pix[k] * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
+                }
+              }
+            } else {
+              // 1-2 rows per thread: row-major with all 8 chunks of a row unrolled (more loads of the constants, all independent)
+#pragma unroll
+              for (int k = 0; k < MAXR; ++k) {
+                const int r = lt + k * kLoaders;
+                if (pix[k] < 0) continue;   // pad rows stay zero
+                const bool own = store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT;
+                __nv_bfloat16* adst = p.a_out + (size_t)pix[k] * p.a_out_cpitch + s * KCH * 8;
+#pragma unroll
+                for (int j = 0; j < KCH; ++j) {
+                  uint4* slot = reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16);
+                  const uint4 a = transform8(*slot, sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr, sd.lrelu);
+                  if (sc != nullptr || sd.lrelu) *slot = a;
+                  if (own) *reinterpret_cast<uint4*>(adst + j * 8) = a;
+                }
+              }
+            }
+          }
+        } else {
+          // 2x2 max-pooled source: four raw loads per output chunk, one transform (pool_transform8r); chunk-major as above
+          constexpr int MAXR = 3;
+          const int Ws = p.W * 2;
+          const __nv_bfloat16* base[MAXR];
+          int pix[MAXR];
+#pragma unroll
+          for (int k = 0; k < MAXR; ++k) {
+            const int r = lt + k * kLoaders;
+            pix[k] = -1;
+            base[k] = sd.ptr;
+            if (r < P) {
+              const long long vin = vbase + r;
+              bool valid = vin >= 0 && vin < p.vtotal;
+              int f = 0, y = 0, x = 0;
+              if (valid) {
+                const unsigned v = (unsigned)vin;
+                f = (int)(v / (unsigned)HpWp);
+                const unsigned rem = v - (unsigned)f * (unsigned)HpWp;
+                y = (int)(rem / (unsigned)p.Wp);
+                x = (int)(rem - (unsigned)y * (unsigned)p.Wp);
+                valid = (y < p.H) && (x < p.W);
+              }
+              if (valid) {
+                const int fs = sd.frame_map ? __ldg(sd.frame_map + f) : f;
+                base[k] = sd.ptr + (((size_t)fs * (p.H * 2) + 2 * y) * Ws + 2 * x) * sd.cpitch + sd.coff + cloc;
+                pix[k] = (f * p.H + y) * p.W + x;
+              } else {
+#pragma unroll
+                for (int j = 0; j < KCH; ++j) *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = make_uint4(0, 0, 0, 0);
+              }
+            }
+          }
+          const float* sc = sd.scale ? sd.scale + cloc : nullptr;
+          const float* sh = sd.shift ? sd.shift + cloc : nullptr;
+#pragma unroll 2
+          for (int j = 0; j < KCH; ++j) {
+            const Affine8 af = load_affine8(sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr);
+            uint4 raw[MAXR][4];
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+              if (pix[k] < 0) continue;
+              const __nv_bfloat16* b = base[k] + j * 8;
+              raw[k][0] = __ldg(reinterpret_cast<const uint4*>(b));
+              raw[k][1] = __ldg(reinterpret_cast<const uint4*>(b + sd.cpitch));
+              raw[k][2] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)Ws * sd.cpitch));
+              raw[k][3] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(Ws + 1) * sd.cpitch));
+            }
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+              if (pix[k] < 0) continue;
+              const int r = lt + k * kLoaders;
+              const uint4 a = pool_transform8r(raw[k][0], raw[k][1], raw[k][2], raw[k][3], af, sd.lrelu);
               *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = a;
               if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
-                *reinterpret_cast<uint4*>(p.a_out + ((size_t)(f * p.H + y) * p.W + x) * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
-            }
-          } else {
-            const __nv_bfloat16* base;
-            if (sd.mode == SRVP_SRC_UP2) {
-              base = sd.ptr + (((size_t)fs * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * sd.cpitch + sd.coff + cloc;
-            } else {
-              base = sd.ptr + (((size_t)fs * p.H + y) * (sd.row_pitch ? sd.row_pitch : p.W) + x) * sd.cpitch + sd.coff + cloc;
-            }
-            uint4 raw[KCH];
-#pragma unroll
-            for (int j = 0; j < KCH; ++j) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + j * 8));
-            const bool own = store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT;
-            __nv_bfloat16* adst = p.a_out + ((size_t)(f * p.H + y) * p.W + x) * p.a_out_cpitch + s * KCH * 8;
-#pragma unroll
-            for (int j = 0; j < KCH; ++j) {
-              const uint4 a = transform8(raw[j], sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr, sd.lrelu);
-              *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = a;
-              if (own) *reinterpret_cast<uint4*>(adst + j * 8) = a;
+                *reinterpret_cast<uint4*>(p.a_out + (size_t)pix[k] * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
             }
           }
         }
@@ -508,7 +585,7 @@ struct Choice { int NB, MT; };
 // (halves the L2->SM weight stream, the un-overlapped epilogue is < 10 % of such a tile); shallower ones keep 128-pixel tiles
 // with two accumulator stages so that the epilogue hides behind the next tile.
 Choice choose(int cout_padded, int kin = 0) {
-  if (cout_padded <= 16) return {16, 256};
+  if (cout_padded <= 16) return {16, 512};  // HBM-bound thin output: large tiles amortise the per-tile pipeline hand-offs
   if (cout_padded == 64) return {64, 512};
   if (cout_padded % 256 == 0) return {256, kin >= 512 ? 256 : 128};
   if (cout_padded % 128 == 0) return {128, 256};
@@ -585,6 +662,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.num_nblk = a->cout_padded / ch.NB;
   d.num_mtiles = (int)((d.vtotal + ch.MT - 1) / ch.MT);
   d.P = ch.MT + 2 * d.Wp + 2;
+  SRVP_REQUIRE(d.P <= 3 * kLoaders, "conv3x3: halo tile of %d rows exceeds the loader's 3 rows per thread (W=%d)", d.P, a->W);
   d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   d.out_cpitch = a->out_cpitch; d.out_coff = a->out_coff;
   d.stats_partial = a->stats_partial;
@@ -613,7 +691,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   const int sms = num_sms_cached();
   if (a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32) {
     SRVP_REQUIRE(ch.NB == 16 && kper == 64 && a->out_f32_nchw != nullptr, "conv3x3: sigmoid epilogue needs cout<=16, 64-channel stages");
-    return launch<16, 256, 8, 1, SRVP_EPI_SIGMOID_NCHW_F32>(d, stream, sms);
+    return launch<16, 512, 8, 1, SRVP_EPI_SIGMOID_NCHW_F32>(d, stream, sms);
   }
   SRVP_REQUIRE((a->out != nullptr || a->out_raw_f32 != nullptr) && a->out_cpitch % 8 == 0 && a->out_coff % 8 == 0, "conv3x3: bad output tensor");
   if (kper == 16) {
