@@ -362,6 +362,89 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
   }
 }
 
+// Fast path of the same two passes for the plain case (DIRECT da with the layer's own geometry, no skip gradient, dense output):
+// the tensors are flat arrays of 16-byte chunks, a thread keeps ONE channel chunk for its whole grid-stride loop, so there is no
+// per-item index arithmetic beyond one add (the general kernel spends ~180 instructions per chunk, this one ~70).
+template <bool APPLY>
+__global__ void __launch_bounds__(256, 2) bn_bwd_flat_kernel(const BnBwdDev p, long long chunks, const float* __restrict__ gamma,
+                                                            const float* __restrict__ c1, const float* __restrict__ c2) {
+  __shared__ float red[APPLY ? 1 : 256 * 17];
+  constexpr int U = 4;
+  const int cpp = p.C / 8;
+  const int tid = threadIdx.x;
+  const int j = tid % cpp, c0 = j * 8;
+  float sc[8], sh[8], ka[8], kb[8], k0[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = p.scale[c0 + e]; sh[e] = p.shift[c0 + e];
+    const float is = p.invstd[c0 + e], mu = p.mean[c0 + e];
+    if (APPLY) {
+      k0[e] = gamma[c0 + e] * is;
+      ka[e] = -is * k0[e] * c2[c0 + e];
+      kb[e] = k0[e] * (mu * is * c2[c0 + e] - c1[c0 + e]);
+    } else {
+      k0[e] = 0.f; ka[e] = is; kb[e] = mu * is;
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+  const uint4* zp = reinterpret_cast<const uint4*>(p.z);
+  const uint4* dp = reinterpret_cast<const uint4*>(p.da);
+  uint4* gp = reinterpret_cast<uint4*>(p.g);
+  const long long stride = (long long)gridDim.x * 256;   // multiple of cpp: the thread's channel chunk never changes
+  for (long long i = (long long)blockIdx.x * 256 + tid; i < chunks; i += stride * U) {
+    uint4 zv[U], dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + u * stride;
+      if (ii < chunks) { zv[u] = __ldg(zp + ii); dv[u] = __ldg(dp + ii); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + u * stride;
+      if (ii >= chunks) break;
+      float z[8], da[8], o[8];
+      unpack8(zv[u], z);
+      unpack8(dv[u], da);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float pre = fmaf(z[e], sc[e], sh[e]);
+        const float gg = da[e] * ((p.lrelu && !(pre > 0.f)) ? 0.2f : 1.f);
+        if (APPLY) {
+          o[e] = fmaf(k0[e], gg, fmaf(z[e], ka[e], kb[e]));
+        } else {
+          s1[e] += gg;
+          s2[e] = fmaf(gg, fmaf(z[e], ka[e], -kb[e]), s2[e]);
+        }
+      }
+      if (APPLY) gp[ii] = pack8(o);
+    }
+  }
+  if (!APPLY) {
+    const int lanes = 256 / cpp;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { red[tid * 17 + e] = s1[e]; red[tid * 17 + 8 + e] = s2[e]; }
+    __syncthreads();
+    if (tid < cpp) {
+      float a1[8], a2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        const float* r = red + (l * cpp + tid) * 17;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a1[e] += r[e]; a2[e] += r[8 + e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float* dst = p.partial + ((size_t)blockIdx.x * p.C + tid * 8 + e) * 2;
+        dst[0] = a1[e];
+        dst[1] = a2[e];
+      }
+    }
+  }
+}
+
 // c1 = sum(g)/n, c2 = sum(g*xhat)/n; dgamma += sum(g*xhat), dbeta += sum(g). Same block shape as bn_finalize_kernel.
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float* __restrict__ c1,
                                                              float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -695,13 +778,22 @@ static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gam
   d.F = a->frames; d.H = a->H; d.W = a->W; d.C = a->C; d.lrelu = a->lrelu;
   d.g_s2d = a->g_s2d;
   if (a->g_s2d) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "bn_bwd: space-to-depth output needs even size");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->da_mode == SRVP_SRC_DIRECT && a->skip == nullptr && !a->g_s2d && a->da_cpitch == a->C && a->da_coff == 0) {
+    // plain case: flat 16-byte chunks (same grid as the general kernel: srvp_bn_bwd_reduce_rows sizes the partial buffer)
+    const long long pixels = (long long)a->frames * a->H * a->W;
+    const int nbf = bn_bwd_blocks(pixels, a->C, a->da_mode);
+    const long long chunks = pixels * (a->C / 8);
+    if (apply) bn_bwd_flat_kernel<true><<<nbf, 256, 0, st>>>(d, chunks, gamma, c1, c2);
+    else bn_bwd_flat_kernel<false><<<nbf, 256, 0, st>>>(d, chunks, nullptr, nullptr, nullptr);
+    return check_launch(apply ? "bn_bwd_apply" : "bn_bwd_reduce");
+  }
   const bool pooled = a->da_mode == SRVP_SRC_POOL2;
   if (pooled || a->da_mode == SRVP_SRC_UP2) SRVP_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0 || !pooled, "bn_bwd: pooled mode needs even size");
   const long long items = pooled ? (long long)a->frames * (a->H / 2) * (a->W / 2) : (long long)a->frames * a->H * a->W;
   SRVP_REQUIRE(items * 4 < 2000000000LL, "bn_bwd: problem too large for 32-bit pixel indices");
   const int nb = bn_bwd_blocks(items, a->C, a->da_mode);
   const int ipb = (int)((items + nb - 1) / nb);
-  cudaStream_t st = (cudaStream_t)stream;
 #define SRVP_BN_LAUNCH(MODE)                                                                    \
   if (apply) bn_bwd_kernel<MODE, true><<<nb, 256, 0, st>>>(d, (int)items, ipb, gamma, c1, c2);       \
   else bn_bwd_kernel<MODE, false><<<nb, 256, 0, st>>>(d, (int)items, ipb, nullptr, nullptr, nullptr);
