@@ -237,8 +237,12 @@ typedef struct {
   int32_t act;         /* SRVP_ACT_* */
   int32_t accumulate;  /* C += result (fp32 C only) */
   int32_t split_k;     /* 0 = automatic (only splits accumulate-mode problems) */
+  int64_t split_stride;/* > 0 (with split_k >= 1, fp32 C, no bias/act/accumulate): K slice z writes its partial result at C + z*split_stride
+                          with plain stores (deterministic split-K); sum the planes with srvp_sum_slices_f32 */
 } srvp_gemm_args;
 int srvp_gemm(const srvp_gemm_args* args, void* stream);
+/* out[i] = sum over s < nslices of in[s*n + i] (fp32, fixed order). */
+int srvp_sum_slices_f32(const float* in, float* out, int32_t nslices, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Inference networks in fp32 on the CUDA cores (they feed the KL terms; < 0.1 % of the FLOPs): the small dense layers

@@ -50,7 +50,7 @@ class GemmArgs(ctypes.Structure):
     _fields_ = [('a', c_ptr), ('a_dtype', c_int), ('a_sm', c_i64), ('a_sk', c_i64), ('b', c_ptr), ('b_dtype', c_int),
                 ('b_sn', c_i64), ('b_sk', c_i64), ('c', c_ptr), ('c_dtype', c_int), ('c_sm', c_i64), ('c_sn', c_i64),
                 ('bias', c_ptr), ('bias_on_m', c_int), ('M', c_int), ('N', c_int), ('K', c_int), ('act', c_int),
-                ('accumulate', c_int), ('split_k', c_int)]
+                ('accumulate', c_int), ('split_k', c_int), ('split_stride', c_i64)]
 
 
 class LinearArgs(ctypes.Structure):
@@ -111,7 +111,7 @@ EXPORTS = [
     'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_launch_count', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
     'srvp_pack_conv3x3_weights', 'srvp_pack_conv4x4s2_weights', 'srvp_conv4x4s2_tap_mask', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16',
     'srvp_nchw_f32_to_s2d_bf16', 'srvp_sigmoid_bwd_nchw_to_s2d16', 'srvp_nhwc_bf16_to_nchw_f32',
-    'srvp_materialize_src', 'srvp_sum_over_time_bf16', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
+    'srvp_materialize_src', 'srvp_sum_over_time_bf16', 'srvp_sum_slices_f32', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
     'srvp_bn_tanh_rows_bwd_apply',

@@ -82,6 +82,14 @@ __global__ void sum_over_time_kernel(const __nv_bfloat16* __restrict__ in, __nv_
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+__global__ void sum_slices_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int nslices, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < nslices; ++s) acc += __ldg(in + (long long)s * n + i);
+  out[i] = acc;
+}
+
 // Materialises a fused source (BN apply + LeakyReLU + pool/upsample + frame gather) as NHWC bf16.
 __global__ void materialize_src_kernel(const SrcDev sd, __nv_bfloat16* __restrict__ out, long long total_chunks, int H, int W, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,6 +709,12 @@ extern "C" int srvp_nhwc_bf16_to_nchw_f32(const srvp_bf16* in, float* out, int32
   const long long total = (long long)frames * C * H * W;
   nhwc_bf16_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, total, C, H * W, cpitch);
   return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int srvp_sum_slices_f32(const float* in, float* out, int32_t nslices, int64_t n, void* stream) {
+  SRVP_REQUIRE(in && out && nslices > 0 && n > 0, "sum_slices: bad argument");
+  sum_slices_f32_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, nslices, n);
+  return check_launch("sum_slices");
 }
 
 extern "C" int srvp_sum_over_time_bf16(const srvp_bf16* in, srvp_bf16* out, int32_t nt, int64_t n, void* stream) {

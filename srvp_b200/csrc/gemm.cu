@@ -26,6 +26,7 @@ struct GemmDev {
   int M, N, K;
   int act, accumulate, bias_on_m;
   int ksteps_total, ksteps_per_split;
+  long long c_split_stride;  // > 0: split z writes its own partial result at c + z * stride (plain stores, deterministic)
 };
 
 // 8 consecutive elements starting at element index `idx` (nvalid of them in bounds) -> packed bf16.
@@ -157,10 +158,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmDev p) 
             if (add_bias && !p.bias_on_m) x += __ldg(p.bias + n);
             if (p.act == 1) x = fmaxf(x, 0.f);
             else if (p.act == 2) x = tanhf(x);
-            const long long idx = (long long)m * p.c_sm + (long long)n * p.c_sn;
+            const long long idx = (long long)m * p.c_sm + (long long)n * p.c_sn + (long long)blockIdx.z * p.c_split_stride;
             if (p.c_f32) {
               float* dst = reinterpret_cast<float*>(p.c) + idx;
-              if (gridDim.z > 1) atomicAdd(dst, x);
+              if (p.c_split_stride > 0) *dst = x;
+              else if (gridDim.z > 1) atomicAdd(dst, x);
               else if (p.accumulate) *dst += x;
               else *dst = x;
             } else {
@@ -204,9 +206,18 @@ extern "C" int srvp_gemm(const srvp_gemm_args* g, void* stream) {
       while (mt * nt * split < sms && d.ksteps_total / (split * 2) >= 4) split *= 2;
     }
   }
-  if (split > 1) SRVP_REQUIRE(g->accumulate && d.c_f32 && g->act == 0, "gemm: split-K needs accumulate into fp32 without activation");
+  d.c_split_stride = 0;
+  if (g->split_stride > 0) {
+    // deterministic split-K: split_k slices of the reduction, each written to its own (M, N) plane; the caller sums the planes
+    SRVP_REQUIRE(g->split_k >= 1 && d.c_f32 && g->act == 0 && !g->accumulate && g->bias == nullptr, "gemm: partial planes need plain fp32 output");
+    d.c_split_stride = g->split_stride;
+  } else if (split > 1) {
+    SRVP_REQUIRE(g->accumulate && d.c_f32 && g->act == 0, "gemm: split-K needs accumulate into fp32 without activation");
+  }
   d.ksteps_per_split = (d.ksteps_total + split - 1) / split;
+  const int split_req = split;
   split = (d.ksteps_total + d.ksteps_per_split - 1) / d.ksteps_per_split;
+  if (g->split_stride > 0) SRVP_REQUIRE(split == split_req, "gemm: %d K steps do not divide into %d non-empty slices", d.ksteps_total, split_req);
   const size_t smem = GSTAGES * 2 * OP_BYTES + 16 * 8 + 16;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }

@@ -153,7 +153,8 @@ def _encoder_head_fwd(enc, c, prev, mode, training, want_stats_update):
     c.a_last = ops.materialize(Src(prev.tensor, C, prev.scale, prev.shift, None, 0, mode, True), F_, 4, 4)  # (F,4,4,C)
     c.wl = ops.transpose_last2(conv_l.weight.view(enc.nh, C, 16))  # (nh, 16, C) = [co][(y,x)][c]
     c.z_last = torch.empty(F_, enc.nh, dtype=torch.float32, device=dev)
-    ops.gemm(c.a_last.view(F_, 16 * C), c.wl.view(enc.nh, 16 * C), c.z_last)
+    # few output tiles (F/128 x 1) and a reduction of 16*C: deterministic split-K over 8 slices
+    ops.gemm(c.a_last.view(F_, 16 * C), c.wl.view(enc.nh, 16 * C), c.z_last, det_split=8 if (16 * C) % (8 * 64) == 0 else 0)
     c.st_last = BNState(enc.nh, dev)
     c.hx = ops.bn_tanh_rows_fwd(c.z_last, bn_l, c.st_last, training, update_running=want_stats_update)
     if training and want_stats_update:
@@ -385,7 +386,7 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads):
     nin, C0 = up_conv.in_channels, up_conv.out_channels
     dz0 = ops.bn_bwd(c.z0, c.st0, up_bn.weight, grads[1], grads[2], da, da_mode, F_, 4, 4, C0, da_coff=0, sync=ops.is_sync_bn(up_bn))
     d_inp = torch.empty(F_, nin, dtype=torch.float32, device=dev)
-    ops.gemm(dz0.view(F_, 16 * C0), c.wp0.view(nin, 16 * C0), d_inp)
+    ops.gemm(dz0.view(F_, 16 * C0), c.wp0.view(nin, 16 * C0), d_inp, det_split=8 if (16 * C0) % (8 * 64) == 0 else 0)
     dwp = torch.zeros(nin, 16, C0, dtype=torch.float32, device=dev)
     ops.gemm(c.dec_inp.t(), dz0.view(F_, 16 * C0).t(), dwp.view(nin, 16 * C0), accumulate=True)
     grads[0] = ops.transpose_last2(dwp).view_as(up_conv.weight)

@@ -462,11 +462,29 @@ def _dt(t):
 
 
 @profiled('gemm')
-def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=False, split_k=0):
-    """c[m, n] (+)= act(sum_k a[m, k] * b[n, k] + bias). a, b, c are 2-D (possibly transposed) views of CUDA tensors."""
+def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=False, split_k=0, det_split=0):
+    """c[m, n] (+)= act(sum_k a[m, k] * b[n, k] + bias). a, b, c are 2-D (possibly transposed) views of CUDA tensors.
+
+    det_split > 1: deterministic split-K for long reductions with few output tiles (plain fp32 c): the K range is cut into det_split
+    slices computed by different CTAs into partial planes that are then summed in a fixed order."""
     M, K = a.shape
     N, K2 = b.shape
     assert K == K2 and tuple(c.shape) == (M, N), (a.shape, b.shape, c.shape)
+    if det_split > 1:
+        assert c.dtype == torch.float32 and c.is_contiguous() and bias is None and not accumulate and act == _lib.ACT_NONE
+        planes = torch.empty(det_split, M, N, dtype=torch.float32, device=c.device)
+        _gemm_call(a, b, planes[0], None, False, act, False, det_split, M * N)
+        check(lib().srvp_sum_slices_f32(ptr(planes), ptr(c), c_int(det_split), c_i64(M * N), stream_ptr()), 'sum_slices')
+        _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N)
+        return c
+    _gemm_call(a, b, c, bias, bias_on_m, act, accumulate, split_k, 0)
+    _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N)
+    return c
+
+
+def _gemm_call(a, b, c, bias, bias_on_m, act, accumulate, split_k, split_stride):
+    M, K = a.shape
+    N = b.shape[0]
     g = _lib.GemmArgs()
     g.a, g.a_dtype, g.a_sm, g.a_sk = ctypes.c_void_p(a.data_ptr()), _dt(a), a.stride(0), a.stride(1)
     g.b, g.b_dtype, g.b_sn, g.b_sk = ctypes.c_void_p(b.data_ptr()), _dt(b), b.stride(0), b.stride(1)
@@ -476,10 +494,8 @@ def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=F
     g.bias = ptr(bias)
     g.bias_on_m = int(bias_on_m)
     g.M, g.N, g.K = M, N, K
-    g.act, g.accumulate, g.split_k = act, int(accumulate), split_k
+    g.act, g.accumulate, g.split_k, g.split_stride = act, int(accumulate), split_k, split_stride
     check(lib().srvp_gemm(ctypes.byref(g), stream_ptr()), 'gemm')
-    _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N)
-    return c
 
 
 @profiled('bn_tanh_rows_fwd')
