@@ -263,13 +263,37 @@ typedef struct {
   int32_t M, N, K;
   int32_t act;         /* SRVP_ACT_* */
   int32_t accumulate;  /* C += result (no activation) */
+  int32_t split_k;     /* > 1: deterministic split-K for long reductions with few output tiles: K slice z writes a partial (M, N) plane at
+                          C + z*split_stride (no bias / act / accumulate); the call RETURNS the number of planes written (>= 1), which the
+                          caller sums with srvp_sum_slices_f32 */
+  int64_t split_stride;
 } srvp_linear_args;
-int srvp_linear_f32(const srvp_linear_args* args, void* stream);
+int srvp_linear_f32(const srvp_linear_args* args, void* stream); /* returns 0, a negative error, or the plane count when split_k > 1 */
 int srvp_act_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, int32_t act, void* stream);
 int srvp_lstm_fwd(const float* xproj, const float* whh_t, float* h_all, float* c_all, float* gates, int32_t T, int32_t B, int32_t H,
                   void* stream);
 int srvp_lstm_bwd(const float* dh_all, const float* gates, const float* c_all, const float* whh, float* dgates, int32_t T, int32_t B,
                   int32_t H, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Edges of the training step next to the path and the reparameterised sampling.
+ *   srvp_u8_to_nhwc_bf16  uint8 (B, T, H, W, C) videos as stored by the datasets -> (T*B, H, W, cpad) bf16 in [0,1] (zero padded
+ *                         channels): replaces collate_fn's float conversion / transposes (data/base.py:76-83) and the fp32 H2D copy
+ *                         of train.py:84 by a 4x smaller uint8 copy + one kernel.
+ *   srvp_rsample_fwd/bwd  out = mu + (softplus(rho) + 1e-8) * eps from raw (rows, 2d) parameters (mu | rho) (module/utils.py:88-134,
+ *                         srvp.py:277, :297); bwd: dparams = (g | g * eps * softplus'(rho)).
+ *   srvp_adam_multi       torch.optim.Adam step (train.py:289; no weight decay / amsgrad) over a device table of ntensors rows
+ *                         [param, grad, exp_avg, exp_avg_sq] (uint64 pointers), sizes[], chunk_start[] (first block of each tensor,
+ *                         srvp_adam_chunk() elements per block), nblocks = total blocks; `step` is the 1-based step count.
+ * ---------------------------------------------------------------------------------------------- */
+int srvp_u8_to_nhwc_bf16(const uint8_t* in, srvp_bf16* out, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, int32_t cpad, void* stream);
+/* Same input -> (T, B, C, H, W) fp32 in [0,1], the tensor the reference's training loop hands to the model (train.py:84-88). */
+int srvp_u8_to_tbchw_f32(const uint8_t* in, float* out, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, void* stream);
+int srvp_rsample_fwd(const float* params, const float* eps, int64_t rows, int32_t d, float* out, void* stream);
+int srvp_rsample_bwd(const float* params, const float* eps, const float* g, int64_t rows, int32_t d, float* dparams, void* stream);
+int srvp_adam_chunk(void);
+int srvp_adam_multi(const uint64_t* table, const int64_t* sizes, const int32_t* chunk_start, int32_t ntensors, int32_t nblocks, double lr,
+                    double beta1, double beta2, double eps, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ELBO terms (loss assembly of train.py:90-106 over module/utils.py:88-112, :137-159) as fused reductions.

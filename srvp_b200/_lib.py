@@ -56,7 +56,7 @@ class GemmArgs(ctypes.Structure):
 class LinearArgs(ctypes.Structure):
     _fields_ = [('a', c_ptr), ('a_sm', c_i64), ('a_sk', c_i64), ('b', c_ptr), ('b_sn', c_i64), ('b_sk', c_i64), ('c', c_ptr),
                 ('c_sm', c_i64), ('c_sn', c_i64), ('bias', c_ptr), ('bias2', c_ptr), ('M', c_int), ('N', c_int), ('K', c_int),
-                ('act', c_int), ('accumulate', c_int)]
+                ('act', c_int), ('accumulate', c_int), ('split_k', c_int), ('split_stride', c_i64)]
 
 
 MAX_MLP_LAYERS = 6
@@ -115,6 +115,7 @@ EXPORTS = [
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
     'srvp_bn_tanh_rows_bwd_apply',
+    'srvp_u8_to_nhwc_bf16', 'srvp_u8_to_tbchw_f32', 'srvp_rsample_fwd', 'srvp_rsample_bwd', 'srvp_adam_chunk', 'srvp_adam_multi',
     'srvp_nll_fwd', 'srvp_nll_bwd', 'srvp_kl_normal_fwd', 'srvp_l2_rows_fwd', 'srvp_scale_by_scalar_f32',
     'srvp_linear_f32', 'srvp_act_bwd_f32', 'srvp_lstm_fwd', 'srvp_lstm_bwd',
     'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum',

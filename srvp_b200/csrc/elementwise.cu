@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
       // registers that two resident blocks per SM allow)
       int am[8];
       if (POOLED) {
+        // arg-max of the pooled activation = arg-max (scale >= 0) or arg-min (scale < 0) of the RAW values: BN affine, LeakyReLU and the
+        // bf16 rounding are monotone per channel, so no activation has to be recomputed here; the first extremum wins like torch's
+        // max_pool2d backward (exactly the element the forward loader's min/max selected, see pool_transform8r)
         float best[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; am[e] = 0; }
@@ -310,9 +313,7 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
           unpack8(zvv[u][q], zq);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float v = fmaf(zq[e], sc[e], sh[e]);
-            if (p.lrelu) v = lrelu(v);
-            v = bf16_round(v);  // the forward max-pool compared bf16-rounded activations; first maximum wins
+            const float v = sc[e] >= 0.f ? zq[e] : -zq[e];
             if (v > best[e]) { best[e] = v; am[e] = q; }
           }
         }

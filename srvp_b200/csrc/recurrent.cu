@@ -27,6 +27,8 @@ struct LinDev {
   float* c; long long c_sm, c_sn;
   const float* bias; const float* bias2;
   int M, N, K, act, accumulate;
+  int k_per_split;            // K range of blockIdx.z: [z*k_per_split, min(K, (z+1)*k_per_split))
+  long long c_split_stride;   // blockIdx.z writes its partial result at c + z*stride (deterministic split-K), 0 = no split
 };
 
 __global__ void __launch_bounds__(256) linear_f32_kernel(const LinDev p) {
@@ -39,19 +41,20 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinDev p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += LK) {
+  const int kbeg = blockIdx.z * p.k_per_split, kend = min(p.K, kbeg + p.k_per_split);
+  for (int k0 = kbeg; k0 < kend; k0 += LK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 256;
       {
         const int kk = a_kc ? (idx & 15) : (idx >> 6), mm = a_kc ? (idx >> 4) : (idx & 63);
         const int m = m0 + mm, k = k0 + kk;
-        As[kk][mm] = (m < p.M && k < p.K) ? __ldg(p.a + m * p.a_sm + k * p.a_sk) : 0.f;
+        As[kk][mm] = (m < p.M && k < kend) ? __ldg(p.a + m * p.a_sm + k * p.a_sk) : 0.f;
       }
       {
         const int kk = b_kc ? (idx & 15) : (idx >> 6), nn = b_kc ? (idx >> 4) : (idx & 63);
         const int n = n0 + nn, k = k0 + kk;
-        Bs[kk][nn] = (n < p.N && k < p.K) ? __ldg(p.b + n * p.b_sn + k * p.b_sk) : 0.f;
+        Bs[kk][nn] = (n < p.N && k < kend) ? __ldg(p.b + n * p.b_sn + k * p.b_sk) : 0.f;
       }
     }
     __syncthreads();
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinDev p) {
       if (p.bias2) v += __ldg(p.bias2 + n);
       if (p.act == SRVP_ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == SRVP_ACT_TANH) v = tanhf(v);
-      float* dst = p.c + m * p.c_sm + n * p.c_sn;
+      float* dst = p.c + m * p.c_sm + n * p.c_sn + (long long)blockIdx.z * p.c_split_stride;
       *dst = p.accumulate ? *dst + v : v;
     }
   }
@@ -222,10 +225,19 @@ extern "C" int srvp_linear_f32(const srvp_linear_args* a, void* stream) {
   SRVP_REQUIRE(a != nullptr && a->a && a->b && a->c, "linear_f32: null argument");
   SRVP_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "linear_f32: empty problem %d x %d x %d", a->M, a->N, a->K);
   SRVP_REQUIRE(!(a->accumulate && a->act != SRVP_ACT_NONE), "linear_f32: accumulate excludes an activation");
-  LinDev d{a->a, a->a_sm, a->a_sk, a->b, a->b_sn, a->b_sk, a->c, a->c_sm, a->c_sn, a->bias, a->bias2, a->M, a->N, a->K, a->act, a->accumulate};
-  dim3 grid((a->N + LT - 1) / LT, (a->M + LT - 1) / LT);
+  int split = a->split_k > 1 ? a->split_k : 1;
+  if (split > 1)
+    SRVP_REQUIRE(a->split_stride > 0 && a->bias == nullptr && a->bias2 == nullptr && a->act == SRVP_ACT_NONE && !a->accumulate,
+                 "linear_f32: split-K writes plain partial planes (no bias / activation / accumulate)");
+  int kper = (a->K + split - 1) / split;
+  kper = (kper + LK - 1) / LK * LK;
+  split = (a->K + kper - 1) / kper;   // planes beyond this are not written: the caller sums `split` planes (returned)
+  LinDev d{a->a, a->a_sm, a->a_sk, a->b, a->b_sn, a->b_sk, a->c, a->c_sm, a->c_sn, a->bias, a->bias2, a->M, a->N, a->K, a->act, a->accumulate,
+           kper, split > 1 ? a->split_stride : 0};
+  dim3 grid((a->N + LT - 1) / LT, (a->M + LT - 1) / LT, split);
   linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
-  return check_launch("linear_f32");
+  const int rc = check_launch("linear_f32");
+  return rc != 0 ? rc : (a->split_k > 1 ? split : 0);   // number of partial planes written (0 when not split)
 }
 
 extern "C" int srvp_act_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, int32_t act, void* stream) {

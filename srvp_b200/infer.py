@@ -18,11 +18,30 @@ _ACT = {None: _lib.ACT_NONE, 'relu': _lib.ACT_RELU, 'tanh': _lib.ACT_TANH}
 
 @profiled('linear_f32')
 def matmul_f32(a, b, c, *, bias=None, bias2=None, act=_lib.ACT_NONE, accumulate=False):
-    """c[m, n] (+)= act(sum_k a[m, k] * b[n, k] + bias[n] + bias2[n]); a, b, c: 2-D fp32 (possibly transposed) views."""
+    """c[m, n] (+)= act(sum_k a[m, k] * b[n, k] + bias[n] + bias2[n]); a, b, c: 2-D fp32 (possibly transposed) views.
+    Long reductions with few 64x64 output tiles (weight gradients over T*B rows) are split over K into partial planes that are summed
+    in a fixed order (deterministic)."""
     M, K = a.shape
     N, K2 = b.shape
     assert K == K2 and tuple(c.shape) == (M, N), (a.shape, b.shape, c.shape)
     assert a.dtype == b.dtype == c.dtype == torch.float32 and a.is_cuda
+    tiles = ((M + 63) // 64) * ((N + 63) // 64)
+    split = 1
+    if bias is None and bias2 is None and act == _lib.ACT_NONE and not accumulate and c.is_contiguous():
+        while tiles * split < 128 and K // (split * 2) >= 128:
+            split *= 2
+    if split > 1:
+        planes = torch.empty(split, M, N, dtype=torch.float32, device=c.device)
+        g = _lib.LinearArgs()
+        g.a, g.a_sm, g.a_sk = ctypes.c_void_p(a.data_ptr()), a.stride(0), a.stride(1)
+        g.b, g.b_sn, g.b_sk = ctypes.c_void_p(b.data_ptr()), b.stride(0), b.stride(1)
+        g.c, g.c_sm, g.c_sn = ctypes.c_void_p(planes.data_ptr()), N, 1
+        g.M, g.N, g.K, g.act, g.accumulate, g.split_k, g.split_stride = M, N, K, act, 0, split, M * N
+        nplanes = lib().srvp_linear_f32(ctypes.byref(g), stream_ptr())
+        if nplanes <= 0:
+            check(nplanes if nplanes < 0 else -1, 'linear_f32 (split)')
+        check(lib().srvp_sum_slices_f32(ptr(planes), ptr(c), c_int(nplanes), c_i64(M * N), stream_ptr()), 'sum_slices')
+        return c
     g = _lib.LinearArgs()
     g.a, g.a_sm, g.a_sk = ctypes.c_void_p(a.data_ptr()), a.stride(0), a.stride(1)
     g.b, g.b_sn, g.b_sk = ctypes.c_void_p(b.data_ptr()), b.stride(0), b.stride(1)
@@ -130,3 +149,31 @@ def lstm(x, lstm_container):
     """Applies an nn.LSTM(., ., 1) container to x (T, B, I); returns the hidden states (T, B, H)."""
     assert lstm_container.num_layers == 1 and not lstm_container.bidirectional
     return LSTMFn.apply(x, lstm_container.weight_ih_l0, lstm_container.weight_hh_l0, lstm_container.bias_ih_l0, lstm_container.bias_hh_l0)
+
+
+class RsampleFn(torch.autograd.Function):
+    """z = mu + (softplus(rho) + 1e-8) * eps from raw parameters (..., 2d) = (mu | rho) (module/utils.py:88-134)."""
+
+    @staticmethod
+    def forward(ctx, params, eps):
+        params, eps = params.contiguous(), eps.contiguous()
+        d = params.shape[-1] // 2
+        rows = params.numel() // (2 * d)
+        assert eps.numel() == rows * d and params.dtype == eps.dtype == torch.float32
+        out = torch.empty(*params.shape[:-1], d, dtype=torch.float32, device=params.device)
+        check(lib().srvp_rsample_fwd(ptr(params), ptr(eps), c_i64(rows), c_int(d), ptr(out), stream_ptr()), 'rsample_fwd')
+        ctx.save_for_backward(params, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        params, eps = ctx.saved_tensors
+        d = params.shape[-1] // 2
+        dparams = torch.empty_like(params)
+        check(lib().srvp_rsample_bwd(ptr(params), ptr(eps), ptr(g.contiguous()), c_i64(params.numel() // (2 * d)), c_int(d), ptr(dparams),
+                                    stream_ptr()), 'rsample_bwd')
+        return dparams, None
+
+
+def rsample(params, eps):
+    return RsampleFn.apply(params, eps)

@@ -59,9 +59,8 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         return torch.empty(shape, dtype=torch.float32, device=like.device).normal_()
 
     def _rsample(self, raw_params):
-        loc, raw_scale = torch.chunk(raw_params, 2, -1)
-        scale = nn.functional.softplus(raw_scale) + 1e-8
-        return loc + self._normal(loc.shape, loc) * scale
+        shape = (*raw_params.shape[:-1], raw_params.shape[-1] // 2)
+        return infer.rsample(raw_params, self._normal(shape, raw_params))
 
     # ------------------------------------------------------------------------------------------------ encode / decode
     def _encode_fused(self, x):
@@ -157,8 +156,7 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         eps = torch.stack([self._normal((bsz, self.nz), y_0) for _ in range(nt - 1)]) if nt > 1 else None
         if n_post > 0:
             q_z_params = infer.linear(hx_z[1:n_post + 1], self.q_z)
-            loc, raw_scale = torch.chunk(q_z_params, 2, -1)
-            z_post = loc + eps[:n_post] * (nn.functional.softplus(raw_scale) + 1e-8)
+            z_post = infer.rsample(q_z_params, eps[:n_post])
         y_all, p_z_params, z, res = latent.latent_loop(self.p_z, self.dynamics, y_0, z_post, eps, nt, oversampling, float(dt), n_post,
                                                         self.nh_res)
         y = y_all[::oversampling] if remove_intermediate else y_all

@@ -273,6 +273,27 @@ def nchw_to_s2d_bf16(x, cpad):
     return out
 
 
+@profiled('u8_to_nhwc_bf16')
+def u8_to_nhwc_bf16(videos_u8, cpad):
+    """uint8 (B, T, H, W, C) on the device -> ((T*B, H, W, cpad) bf16 in [0, 1], frames ordered (t, b) as x.view(T*B, ...))."""
+    assert videos_u8.dtype == torch.uint8 and videos_u8.is_cuda and videos_u8.is_contiguous()
+    B, T, H, W, C = videos_u8.shape
+    out = torch.empty(T * B, H, W, cpad, dtype=torch.bfloat16, device=videos_u8.device)
+    check(lib().srvp_u8_to_nhwc_bf16(ptr(videos_u8), ptr(out), c_int(B), c_int(T), c_int(H), c_int(W), c_int(C), c_int(cpad), stream_ptr()),
+          'u8_to_nhwc')
+    return out
+
+
+@profiled('u8_to_tbchw_f32')
+def u8_to_tbchw_f32(videos_u8):
+    """uint8 (B, T, H, W, C) on the device -> (T, B, C, H, W) fp32 in [0, 1] (what collate_fn + .to(device) produce, data/base.py:76-83)."""
+    assert videos_u8.dtype == torch.uint8 and videos_u8.is_cuda and videos_u8.is_contiguous()
+    B, T, H, W, C = videos_u8.shape
+    out = torch.empty(T, B, C, H, W, dtype=torch.float32, device=videos_u8.device)
+    check(lib().srvp_u8_to_tbchw_f32(ptr(videos_u8), ptr(out), c_int(B), c_int(T), c_int(H), c_int(W), c_int(C), stream_ptr()), 'u8_to_tbchw')
+    return out
+
+
 @profiled('nchw_to_nhwc_bf16')
 def nchw_to_nhwc_bf16(x, cpad):
     """(frames, C, H, W) fp32 -> (frames, H, W, cpad) bf16, zero padded channels."""

@@ -6,7 +6,8 @@ import bench
 from srvp_b200.module.srvp import StochasticLatentResidualVideoPredictor
 torch.manual_seed(1)
 m = StochasticLatentResidualVideoPredictor(*[bench.CFG[k] for k in bench.ARG_ORDER]); m.init(); m = m.cuda().train(); m.noise_device = 'cuda'
-opt = torch.optim.Adam(m.parameters(), lr=3e-4, fused=True)
+from srvp_b200.optim import Adam
+opt = Adam(m.parameters(), lr=3e-4)
 x = torch.rand(12, 192, 3, 64, 64, device='cuda')
 nt, dt = 12, 0.5
 marks = []

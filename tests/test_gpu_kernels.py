@@ -147,8 +147,7 @@ def test_bn_lrelu_pool_backward(dev, mode, with_skip, C, H):
     beta = (torch.randn(C, device=dev) * 0.2).requires_grad_(True)
     zf = z.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     a = F.leaky_relu(F.batch_norm(zf, None, None, gamma, beta, True, 0.0, 1e-5), 0.2)
-    a_r = a.detach().to(torch.bfloat16).float() + (a - a.detach())   # the forward pool compares bf16-rounded activations
-    out = F.max_pool2d(a_r, 2) if mode == 1 else F.interpolate(a, scale_factor=2, mode='nearest') if mode == 2 else a
+    out = F.max_pool2d(a, 2) if mode == 1 else F.interpolate(a, scale_factor=2, mode='nearest') if mode == 2 else a
     da = (torch.randn_like(out) * 0.1).to(torch.bfloat16)
     bn = _BN()
     bn.weight, bn.bias = gamma.detach(), beta.detach()
@@ -363,3 +362,50 @@ def test_fused_elbo_matches_torch_distributions(dev):
         assert float(a) == pytest.approx(float(b), rel=2e-6)
     for a, t in zip(g1, (x_, qy, qz, pz, res)):
         assert rel(a, t.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ training-step edges
+def test_adam_multi_matches_torch_adam(dev):
+    """srvp_b200.optim.Adam (one launch for all tensors) against torch.optim.Adam over 5 steps, with an LR scheduler in the loop."""
+    from srvp_b200.optim import Adam
+    shapes = [(64, 3, 3, 3), (64,), (512, 1024, 3, 3), (1, ), (100, 512), (33333,)]
+    g = torch.Generator().manual_seed(2)
+    p1 = [torch.nn.Parameter(torch.randn(*s, generator=g).to(dev)) for s in shapes]
+    p2 = [torch.nn.Parameter(p.detach().clone()) for p in p1]
+    o1, o2 = Adam(p1, lr=3e-4), torch.optim.Adam(p2, lr=3e-4)
+    s1 = torch.optim.lr_scheduler.LambdaLR(o1, lr_lambda=lambda i: max(0, (10 - i) / 10))
+    s2 = torch.optim.lr_scheduler.LambdaLR(o2, lr_lambda=lambda i: max(0, (10 - i) / 10))
+    for step in range(5):
+        for a, b in zip(p1, p2):
+            gr = torch.randn(a.shape, generator=g).to(dev) * (10.0 ** (step - 2))
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o1.step(); o2.step(); s1.step(); s2.step()
+    for a, b in zip(p1, p2):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    sd1, sd2 = o1.state_dict(), o2.state_dict()
+    assert set(sd1['state'][0].keys()) == set(sd2['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
+    assert torch.allclose(sd1['state'][2]['exp_avg_sq'], sd2['state'][2]['exp_avg_sq'], rtol=1e-5, atol=1e-12)
+
+
+def test_rsample_and_u8_input(dev):
+    from srvp_b200 import infer, ops
+    params = torch.randn(7, 5, 40, device=dev, requires_grad=True)
+    with torch.no_grad():
+        params[0, 0, 20:] = 30.0
+    eps = torch.randn(7, 5, 20, device=dev)
+    z = infer.rsample(params, eps)
+    p2 = params.detach().clone().requires_grad_(True)
+    loc, rho = p2.chunk(2, -1)
+    z2 = loc + eps * (F.softplus(rho) + 1e-8)
+    assert rel(z, z2) < 1e-6
+    gz = torch.randn_like(z)
+    z.backward(gz); z2.backward(gz)
+    assert rel(params.grad, p2.grad) < 1e-6
+    # uint8 (B, T, H, W, C) -> (T*B, H, W, 16) bf16 in [0, 1]
+    v = torch.randint(0, 256, (3, 4, 64, 64, 3), dtype=torch.uint8, device=dev)
+    out = ops.u8_to_nhwc_bf16(v, 16)
+    ref = torch.zeros(4 * 3, 64, 64, 16, device=dev)
+    ref[..., :3] = (v.float() / 255).permute(1, 0, 2, 3, 4).reshape(12, 64, 64, 3)
+    assert torch.equal(out.float(), bf(ref))
+    x = ops.u8_to_tbchw_f32(v)
+    assert torch.allclose(x, (v.float() / 255).permute(1, 0, 4, 2, 3), rtol=1e-6, atol=0)

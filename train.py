@@ -18,14 +18,20 @@ import numpy as np
 import torch
 import torch.distributions as distrib
 
-from srvp_b200 import elbo
+from srvp_b200 import elbo, ops
+from srvp_b200.optim import Adam
 from srvp_b200.module import srvp, utils
 
 
 def train(forward_fn, optimizer, scaler, batch, device, opt):
     """One optimisation step; returns (loss, nll, kl_y_0, kl_z) batch-averaged (reference train.py:49-129)."""
     optimizer.zero_grad()
-    x = batch.to(device)
+    if batch.dtype == torch.uint8:
+        # (B, T, H, W, C) uint8 as the datasets store it: 4x smaller host->device copy, conversion to the reference's
+        # (T, B, C, H, W) fp32 in [0, 1] on the device (replaces collate_fn's float conversion, data/base.py:76-83)
+        x = ops.u8_to_tbchw_f32(batch.to(device, non_blocking=True))
+    else:
+        x = batch.to(device)
     nt, n = x.shape[0], x.shape[1]
     x_, y, z, _, q_y_0_params, q_z_params, p_z_params, res = forward_fn(x, nt, dt=1 / opt.n_euler_steps)
     # ELBO of train.py:90-106 as fused reductions (srvp_b200/elbo.py); utils.neg_logprob / make_normal_from_raw_params remain for
@@ -39,7 +45,8 @@ def train(forward_fn, optimizer, scaler, batch, device, opt):
 
 
 def make_batches(opt, rank, world):
-    """Infinite iterator of (T, B, C, H, W) fp32 batches in [0, 1] (the range data/base.py:82-83 produces)."""
+    """Infinite iterator of batches: synthetic (T, B, C, H, W) fp32 in [0, 1] (the range data/base.py:82-83 produces), or pinned uint8
+    (B, T, H, W, C) slices of the .npz array (converted on the device by train())."""
     g = torch.Generator().manual_seed(opt.seed + 1000 * rank)
     if opt.dataset == 'synthetic':
         while True:
@@ -47,8 +54,7 @@ def make_batches(opt, rank, world):
     videos = np.load(os.path.join(opt.data_dir, 'videos.npz'))['videos']      # (N, T, H, W, C) uint8
     while True:
         idx = torch.randint(len(videos), (opt.batch_size,), generator=g).numpy()
-        v = torch.from_numpy(videos[idx][:, :opt.seq_len]).permute(1, 0, 4, 2, 3).float() / 255
-        yield v.contiguous()
+        yield torch.from_numpy(np.ascontiguousarray(videos[idx][:, :opt.seq_len])).pin_memory()   # uint8 (B, T, H, W, C)
 
 
 def create_args():
@@ -115,7 +121,7 @@ def main(opt):
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     model.to(device)
-    optimizer = torch.optim.Adam(model.parameters(), lr=opt.lr)
+    optimizer = Adam(model.parameters(), lr=opt.lr)          # torch.optim.Adam semantics (reference train.py:289), one launch
     opt.n_iter = opt.lr_scheduling_burnin + opt.lr_scheduling_n_iter
     n_sched = opt.lr_scheduling_n_iter
     lr_scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda i: max(0, (n_sched - i) / n_sched))
