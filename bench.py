@@ -27,6 +27,20 @@ CFG = dict(nx=64, nc=3, nf=64, nhx=128, ny=50, nz=50, skipco=True, nt_inf=2, nh_
 ARG_ORDER = ['nx', 'nc', 'nf', 'nhx', 'ny', 'nz', 'skipco', 'nt_inf', 'nh_inf', 'nlayers_inf', 'nh_res', 'nlayers_res', 'archi']
 LOSS = dict(obs_scale=0.71, beta_y=1.0, beta_z=1.0, l2_res=1.0)
 SEQ_LEN, BATCH, DT = 12, 192, 0.5
+METRIC = 'frames/sec training step (BAIR 64x64 seq12 bs192)'
+WORKLOAD = 'BAIR VGG64 skipco nc=3 64x64 seq_len=12 batch=192/GPU ny=nz=50 nt_inf=2 n_euler_steps=2; fwd+ELBO+bwd+Adam'
+
+
+def select_workload(name):
+    """'bair' (default, the configuration BASELINE.json's metric is quoted on) or 'smmnist' (configs[1]: DCGAN64, README.md:111), for the record."""
+    global CFG, LOSS, SEQ_LEN, BATCH, DT, METRIC, WORKLOAD
+    if name == 'smmnist':
+        CFG = dict(nx=64, nc=1, nf=64, nhx=128, ny=20, nz=20, skipco=False, nt_inf=5, nh_inf=256, nlayers_inf=3, nh_res=512, nlayers_res=4,
+                   archi='dcgan')
+        LOSS = dict(obs_scale=1.0, beta_y=1.0, beta_z=2.0, l2_res=1.0)
+        SEQ_LEN, BATCH, DT = 15, 128, 1.0
+        METRIC = 'frames/sec training step (smmnist 64x64 seq15 bs128)'
+        WORKLOAD = 'smmnist DCGAN64 nc=1 64x64 seq_len=15 batch=128/GPU ny=nz=20 nt_inf=5 n_euler_steps=1; fwd+ELBO+bwd+Adam'
 
 
 def peaks():
@@ -186,6 +200,12 @@ def run_ours(args):
     roofline = dict(bound='tensor', kernel=dom, achieved=round(achieved, 1), peak=pk['tf'], unit='TFLOP/s', frac=round(achieved / pk['tf'], 4),
                     traffic=None, peak_source=pk['src'] + ' (sustained bf16 cuBLAS)', share_of_kernel_time=round(d['ms'] / tot_ms, 3),
                     launches_per_step=d['launches'] // 2, avg_launch_ms=round(d['ms'] / d['launches'], 4))
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')   # DRAM bytes per launch of each kernel family from the committed ncu capture
+    if os.path.exists(tpath) and WORKLOAD.startswith('BAIR'):
+        tj = json.load(open(tpath))
+        if dom in tj:
+            roofline['traffic'] = tj[dom]['dram_bytes_per_launch']
+            roofline['traffic_source'] = tj[dom]['source']
     roofline['executed'] = round(d['executed_flops'] / (d['ms'] * 1e-3) / 1e12, 1)
     roofline['note'] = ('achieved = dense FLOPs of the reference ops these launches stand for (SURVEY.md 8d) / time; executed = multiply-adds '
                         'actually issued (the convolutions over cat[h, skip] are split per video, DESIGN.md section 4)')
@@ -199,10 +219,10 @@ def run_ours(args):
     if rank != 0:
         return
     frames = SEQ_LEN * BATCH * world
-    line = dict(metric='frames/sec training step (BAIR 64x64 seq12 bs192)', value=round(frames * args.steps / (ms * 1e-3), 1), unit='frames/s',
+    line = dict(metric=METRIC, value=round(frames * args.steps / (ms * 1e-3), 1), unit='frames/s',
                 n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
-                config=dict(workload='BAIR VGG64 skipco nc=3 64x64 seq_len=12 batch=192/GPU ny=nz=50 nt_inf=2 n_euler_steps=2; fwd+ELBO+bwd+Adam',
+                config=dict(workload=WORKLOAD,
                             global_batch=BATCH * world, seq_len=SEQ_LEN, parallelism=f'dp{world}' + (' + SyncBN statistics' if world > 1 else ''),
                             l2='inputs larger than L2: 113 MB batch, >10 GB of activations per step',
                             e2e_input='uint8 frames (B,T,H,W,C) from pinned host memory, converted on the device'),
@@ -253,10 +273,10 @@ def run_reference(args):
     steps, warm = max(1, min(args.steps, 3)), 1
     cb = cpu_baseline(steps=steps, warmup=warm)
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    line = dict(metric='frames/sec training step (BAIR 64x64 seq12 bs192)', value=cb['value'], unit='frames/s', impl='reference',
+    line = dict(metric=METRIC, value=cb['value'], unit='frames/s', impl='reference',
                 n_gpus=world, steps=steps, warmup=warm, ms_per_step=round(SEQ_LEN * 8 / cb['value'] * 1e3, 1), higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='BAIR VGG64 skipco nc=3 64x64 seq_len=12 batch=192/GPU ny=nz=50 nt_inf=2 n_euler_steps=2; fwd+ELBO+bwd+Adam',
+                config=dict(workload=WORKLOAD,
                             global_batch=BATCH * world, seq_len=SEQ_LEN, parallelism='cpu'),
                 cpu_baseline=cb, e2e=dict(value=cb['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -269,7 +289,9 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='bair', choices=['bair', 'smmnist'])
     a = ap.parse_args()
+    select_workload(a.workload)
     if a.impl == 'reference':
         run_reference(a)
     else:
