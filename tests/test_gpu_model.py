@@ -181,3 +181,21 @@ def test_full_size_properties(dev):
         hx1, _ = m.encode(x[:4])
         hx2, _ = m.encode(x[:4, perm])
     assert torch.allclose(hx1[:, perm], hx2, rtol=0, atol=2e-2)
+
+
+def test_batched_sample_rollout_decode_matches_per_sample(dev):
+    """test.py's batched sampling (samples folded into the batch, skips shared through the frame map) decodes exactly what the
+    reference-style per-sample loop decodes from the same latents."""
+    g = load_golden('vgg_skip_nc3')
+    m = build_model(g['cfg'], g['res_gain'], 2).to(dev).eval()
+    B, S, nt = 2, 3, 4
+    x = make_input(3, B, g['cfg']['nc'], 11).to(dev)
+    with torch.no_grad():
+        hx, handle = m._encode_fused(x)
+        w = m.infer_w(hx)
+        y = torch.randn(nt, S * B, g['cfg']['ny'], generator=torch.Generator().manual_seed(3)).to(dev)
+        xb = m._decode_fused(w.repeat(S, 1), y, handle.levels, handle.frame_map.repeat(S), None)
+        skips = m.encode(x)[1]
+        for s in range(S):
+            xs = m.decode(w, y[:, s * B:(s + 1) * B].contiguous(), skips)
+            assert float(((xs - xb[:, s * B:(s + 1) * B]) ** 2).mean()) < 1e-5
