@@ -759,14 +759,14 @@ extern "C" int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, f
 }
 
 // Grid: enough blocks to fill the machine whatever the channel count (a block walks items_per_block pixels x C/8 chunks with 256
-// threads: ~8 loop iterations per thread), bounded by 8192 and by the size of the partial-sum buffer (blocks x C x 2 floats).
+// threads: ~8 loop iterations per thread), bounded by 2048 and by the size of the partial-sum buffer (blocks x C x 2 floats).
 static int bn_bwd_blocks(long long items, int C, int da_mode) {
   const int U = (da_mode == SRVP_SRC_DIRECT) ? 4 : 2;
   const long long chunk_items = items * (C / 8);
   long long nb = (chunk_items + 256LL * U * 8 - 1) / (256LL * U * 8);
   const long long cap = (1 << 20) / C;
   if (nb > cap) nb = cap;
-  if (nb > 8192) nb = 8192;
+  if (nb > 2048) nb = 2048;   // the finalisation walks one partial row per block with 8 row lanes: keep it short
   if (nb < 1) nb = 1;
   return (int)nb;
 }
