@@ -206,6 +206,14 @@ def run_ours(args):
         if dom in tj:
             roofline['traffic'] = tj[dom]['dram_bytes_per_launch']
             roofline['traffic_source'] = tj[dom]['source']
+    # north star: the encoder convolutions against the tensor-core roofline, the decoder against both (its convolutions are tensor
+    # bound); figures of the conv3x3 launches of each stage
+    stages = {}
+    for t, v in prof.get('conv3x3', {}).get('by_stage', {}).items():
+        tf, gb = v['flops'] / (v['ms'] * 1e-3) / 1e12, v['bytes'] / (v['ms'] * 1e-3) / 1e9
+        stages[t] = dict(ms_per_step=round(v['ms'] / 2, 3), tflops=round(tf, 1), frac_tensor=round(tf / pk['tf'], 4), gbs=round(gb, 1),
+                         frac_hbm=round(gb / pk['hbm'], 4))
+    roofline['conv_stages'] = stages
     roofline['executed'] = round(d['executed_flops'] / (d['ms'] * 1e-3) / 1e12, 1)
     roofline['note'] = ('achieved = dense FLOPs of the reference ops these launches stand for (SURVEY.md 8d) / time; executed = multiply-adds '
                         'actually issued (the convolutions over cat[h, skip] are split per video, DESIGN.md section 4)')

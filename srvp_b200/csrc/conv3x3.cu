@@ -20,6 +20,7 @@
 // Warp roles (persistent CTA, 448 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-11
 // activation loaders, warp 12 MMA issuer (one thread), warp 13 weight TMA-bulk issuer (one thread).
 // TMEM: 2 accumulator stages x (MT/128) x NB fp32 columns, so the epilogue of tile i overlaps tile i+1.
+#include <cstdlib>
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "../../include/srvp_b200.h"
@@ -54,6 +55,8 @@ struct ConvDev {
   int out_row_pitch, out_xstride;  // output pixel index = (f*H + y)*out_row_pitch + x*out_xstride (dense: W, 1)
   int sig_d2s;                     // sigmoid epilogue: columns are (py,px,c) sub-pixel phases of a (F, cout/4, 2H, 2W) image
   int masked;                      // any K stage with fewer than nine taps (4x4 stride-2 family)
+  int wslots;                      // weight-ring slots (Cfg::MIN_WSLOTS .. MAX_WSLOTS, as many as shared memory allows)
+  int dbg;                         // development only (env SRVP_CONV_DBG): 1 = skip activation copies, 2 = skip MMAs, 4 = skip output stores
   uint16_t tap_mask[SRVP_CONV_MAX_STAGES];
 };
 
@@ -76,7 +79,8 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 template <int NB, int MT, int KCH, int TPS, int EPI>
 struct Cfg {
   static constexpr int MBLK = MT / 128;
-  static constexpr int WSLOTS = (KCH != 8) ? 2 : (NB >= 256 ? 3 : 4);
+  static constexpr int MIN_WSLOTS = (KCH != 8) ? 2 : (NB >= 256 ? 3 : 4);  // the host adds slots while shared memory allows (ConvDev.wslots)
+  static constexpr int MAX_WSLOTS = 8;
   static constexpr int SLOT_BYTES = TPS * KCH * NB * 16;
   static constexpr int STAGE_COLS = NB < 128 ? NB : 128;  // output columns staged per pass through shared memory
   static constexpr int STAGE_PITCH = STAGE_COLS * 2 + 16;  // bytes per staged output row
@@ -88,8 +92,8 @@ struct Cfg {
   static constexpr int TMEM_COLS = (ACC_TOTAL <= 32) ? 32 : (ACC_TOTAL <= 64) ? 64 : (ACC_TOTAL <= 128) ? 128 : (ACC_TOTAL <= 256) ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(9 % TPS == 0, "taps per slot must divide 9");
-  static size_t smem_bytes(int P) {
-    return (size_t)kHaloStages * KCH * P * 16 + (size_t)WSLOTS * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 2 * NB * 2 * 4 + 64 * 8 + 16;
+  static size_t smem_bytes(int P, int wslots) {
+    return (size_t)kHaloStages * KCH * P * 16 + (size_t)wslots * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 2 * NB * 2 * 4 + 64 * 8 + 16;
   }
 };
 
@@ -100,15 +104,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   const int P = p.P;
   uint8_t* halo = smem;
   uint8_t* wslots = halo + (size_t)kHaloStages * KCH * P * 16;
-  uint8_t* staging = wslots + (size_t)C::WSLOTS * C::SLOT_BYTES;
+  const int WS = p.wslots;  // weight-ring depth: the ring round trip (MMA commit -> refill from L2 -> MMA) is ~1 us, it must cover it
+  uint8_t* staging = wslots + (size_t)WS * C::SLOT_BYTES;
   int* rowpix = reinterpret_cast<int*>(staging + C::STAGING_BYTES);
   float* statbuf = reinterpret_cast<float*>(rowpix + 128);  // [2 N blocks][NB][2]: per-CTA running (sum, sumsq)
   uint64_t* bars = reinterpret_cast<uint64_t*>(statbuf + 2 * NB * 2);
   uint64_t* halo_full = bars;                    // [kHaloStages]
   uint64_t* halo_empty = bars + kHaloStages;     // [kHaloStages]
   uint64_t* w_full = bars + 2 * kHaloStages;     // [WSLOTS]
-  uint64_t* w_empty = w_full + C::WSLOTS;        // [WSLOTS]
-  uint64_t* acc_full = w_empty + C::WSLOTS;      // [2]
+  uint64_t* w_empty = w_full + C::MAX_WSLOTS;    // [WSLOTS]
+  uint64_t* acc_full = w_empty + C::MAX_WSLOTS;  // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 64);
 
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
 
   if (tid == 0) {
     for (int i = 0; i < kHaloStages; ++i) { mbar_init(&halo_full[i], kLoaders); mbar_init(&halo_empty[i], 1); }
-    for (int i = 0; i < C::WSLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_mbar_init();
   }
@@ -178,7 +183,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               const uint32_t nbytes = valid ? 16u : 0u;
               const int step = valid ? 8 : 0;
 #pragma unroll
-              for (int j = 0; j < KCH; ++j) cp_async16(hbuf + ((size_t)j * P + r) * 16, src + j * step, nbytes);
+              if (!(p.dbg & 1))
+#pragma unroll
+                for (int j = 0; j < KCH; ++j) cp_async16(hbuf + ((size_t)j * P + r) * 16, src + j * step, nbytes);
             }
           }
           cp_async_wait_all();
@@ -286,7 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NB, 0, 0);
-      uint32_t hit = 0, wit = 0, tcount = 0;
+      uint32_t hit = 0, tcount = 0;
+      int ws = 0;          // weight-ring position and phase, advanced incrementally (no divisions on the issuing thread's critical path)
+      uint32_t wph = 0;
       const uint32_t halo_addr = smem_u32(halo), w_addr = smem_u32(wslots);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int as = tcount % C::ACC_STAGES;
@@ -299,32 +308,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           mbar_wait(&halo_full[hs], (hit / kHaloStages) & 1);
           tc_fence_after();
           const uint32_t hbase = halo_addr + hs * KCH * P * 16;
+          const uint64_t ad_stage = umma_desc(hbase, P * 16, 128);
           const uint32_t tmask = (TPS == 1 && p.masked) ? p.tap_mask[s] : 0x1ffu;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             if (!((tmask >> tap) & 1u)) continue;  // 4x4 stride-2 family: this (phase, tap) pair has no weight
             const bool init = fresh;
             fresh = false;
-            const int ws = wit % C::WSLOTS;
             if (tap % TPS == 0) {
-              mbar_wait(&w_full[ws], (wit / C::WSLOTS) & 1);
+              mbar_wait(&w_full[ws], wph);
               tc_fence_after();
             }
             const int ky = tap / 3, kx = tap - 3 * ky;
-            const uint32_t wbase = w_addr + ws * C::SLOT_BYTES + (tap % TPS) * KCH * NB * 16;
+            // descriptors differ only in their start-address field (16-byte units): one base per stage / tap, then plain adds
+            const uint64_t ad_tap = ad_stage + (uint32_t)(ky * p.Wp + kx);
+            const uint64_t bd_tap = umma_desc(w_addr + ws * C::SLOT_BYTES + (tap % TPS) * KCH * NB * 16, NB * 16, 128);
 #pragma unroll
             for (int mb = 0; mb < C::MBLK; ++mb) {
-              const uint32_t abase = hbase + (mb * 128 + ky * p.Wp + kx) * 16;
 #pragma unroll
               for (int k = 0; k < KCH / 2; ++k) {
-                const uint64_t ad = umma_desc(abase + k * 2 * P * 16, P * 16, 128);
-                const uint64_t bd = umma_desc(wbase + k * 2 * NB * 16, NB * 16, 128);
-                umma_bf16(acc + mb * NB, ad, bd, idesc, !(init && k == 0));
+                if (!(p.dbg & 2)) umma_bf16(acc + mb * NB, ad_tap + (uint32_t)(mb * 128) + (uint32_t)(k * 2) * (uint32_t)P, bd_tap + (uint32_t)(k * 2 * NB), idesc, !(init && k == 0));
               }
             }
             if (tap % TPS == TPS - 1) {
               umma_commit(&w_empty[ws]);
-              ++wit;
+              if (++ws == WS) { ws = 0; wph ^= 1u; }
             }
           }
           umma_commit(&halo_empty[hs]);
@@ -335,7 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   } else if (warp == 13) {
     // ------------------------------------------------------------------ weight loader (TMA bulk copies)
     if (lane == 0) {
-      uint32_t wit = 0;
+      int ws = 0;
+      uint32_t wph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nblk = tile % p.num_nblk;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)nblk * p.nstages * 9 * KCH * NB * 16;
@@ -343,11 +352,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           const uint32_t tmask = (TPS == 1 && p.masked) ? p.tap_mask[s] : 0x1ffu;
           for (int q = 0; q < 9 / TPS; ++q) {
             if (TPS == 1 && !((tmask >> q) & 1u)) continue;
-            const int ws = wit % C::WSLOTS;
-            mbar_wait(&w_empty[ws], ((wit / C::WSLOTS) & 1) ^ 1);
+            mbar_wait(&w_empty[ws], wph ^ 1u);
             mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
             bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
-            ++wit;
+            if (++ws == WS) { ws = 0; wph ^= 1u; }
           }
         }
       }
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
               const int r = r0 + lrow;
               const int pix = rowpix[r];
-              if (pix >= 0 && cbase < p.cout && p.out != nullptr) {
+              if (pix >= 0 && cbase < p.cout && p.out != nullptr && !(p.dbg & 4)) {
                 const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
                 *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
               }
@@ -593,9 +601,13 @@ Choice choose(int cout_padded, int kin = 0) {
 }
 
 template <int NB, int MT, int KCH, int TPS, int EPI>
-int launch(const ConvDev& d, cudaStream_t stream, int num_sms) {
+int launch(ConvDev& d, cudaStream_t stream, int num_sms) {
   using C = Cfg<NB, MT, KCH, TPS, EPI>;
-  size_t smem = C::smem_bytes(d.P);
+  int ws = C::MIN_WSLOTS;
+  const int useful = d.nstages * (9 / TPS) * 2;   // more slots than two tiles' worth of transfers buy nothing
+  while (ws < C::MAX_WSLOTS && ws < useful && C::smem_bytes(d.P, ws + 1) <= 226 * 1024) ++ws;
+  d.wslots = ws;
+  size_t smem = C::smem_bytes(d.P, ws);
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM is allocated for a single resident CTA)
   SRVP_REQUIRE(smem <= 227 * 1024, "conv3x3: shared memory %zu B exceeds 227 KB (W=%d)", smem, d.W);
   auto kern = conv3x3_kernel<NB, MT, KCH, TPS, EPI>;
@@ -681,6 +693,11 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.sig_d2s = a->sigmoid_d2s;
   SRVP_REQUIRE(nst <= SRVP_CONV_MAX_STAGES, "conv3x3: %d K stages exceed %d", nst, (int)SRVP_CONV_MAX_STAGES);
   d.masked = 0;
+  {
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("SRVP_CONV_DBG"); dbg_env = e ? atoi(e) : 0; }
+    d.dbg = dbg_env;
+  }
   for (int i = 0; i < nst; ++i) {
     d.tap_mask[i] = a->tap_mask[i] ? (a->tap_mask[i] & 0x1ff) : 0x1ff;
     if (d.tap_mask[i] != 0x1ff) d.masked = 1;

@@ -204,7 +204,9 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
 class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, x, skip_handle, *params):
+        ops.PROFILE_TAG = 'encoder_fwd'
         hx, c = _encoder_fwd(enc, x, enc.training)
+        ops.PROFILE_TAG = ''
         ctx.enc, ctx.c, ctx.skip_handle = enc, c, skip_handle
         if skip_handle is not None:
             if enc._plan == 'dcgan':
@@ -216,7 +218,9 @@ class EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_hx):
+        ops.PROFILE_TAG = 'encoder_bwd'
         grads = _encoder_bwd(ctx.enc, ctx.c, d_hx, ctx.skip_handle)
+        ops.PROFILE_TAG = ''
         ctx.c = None
         return (None, None, None, *grads)
 
@@ -396,13 +400,17 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads):
 class DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dec, dec_inp, skip_levels, frame_map, skip_handle, sel, *params):
+        ops.PROFILE_TAG = 'decoder_fwd'
         x_hat, c = _decoder_fwd(dec, dec_inp.contiguous(), skip_levels, frame_map, dec.training, sel=sel)
+        ops.PROFILE_TAG = ''
         ctx.dec, ctx.c, ctx.skip_handle = dec, c, skip_handle
         return x_hat
 
     @staticmethod
     def backward(ctx, d_xhat):
+        ops.PROFILE_TAG = 'decoder_bwd'
         d_inp, grads = _decoder_bwd(ctx.dec, ctx.c, d_xhat, ctx.skip_handle)
+        ops.PROFILE_TAG = ''
         ctx.c = None
         return (None, d_inp, None, None, None, None, *grads)
 

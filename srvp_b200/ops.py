@@ -13,6 +13,7 @@ from ._lib import c_int, c_i64, check, lib, ptr, stream_ptr
 # bench.py sets PROFILE = {} for a few extra steps: every wrapper below then brackets its launches with CUDA events on the
 # current stream and records (events, algorithmic flops, algorithmic bytes); summarize_profile() reduces them after a sync.
 PROFILE = None
+PROFILE_TAG = ''   # set by the engine around encoder / decoder forward / backward: per-stage roofline figures in bench.py
 
 
 def profiled(name):
@@ -26,7 +27,7 @@ def profiled(name):
             out = fn(*args, **kwargs)
             e1.record()
             fl, by, fx = _WORK.pop()
-            PROFILE.setdefault(name, []).append((e0, e1, fl, by, fx))
+            PROFILE.setdefault(name, []).append((e0, e1, fl, by, fx, PROFILE_TAG))
             return out
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__
@@ -53,6 +54,10 @@ def summarize_profile(profile):
         ms = sum(r[0].elapsed_time(r[1]) for r in recs)
         out[name] = dict(launches=len(recs), ms=ms, flops=sum(r[2] for r in recs), bytes=sum(r[3] for r in recs),
                          executed_flops=sum(r[4] for r in recs))
+        tags = sorted(set(r[5] for r in recs if r[5]))
+        if tags:
+            out[name]['by_stage'] = {t: dict(launches=sum(1 for r in recs if r[5] == t), ms=sum(r[0].elapsed_time(r[1]) for r in recs if r[5] == t),
+                                             flops=sum(r[2] for r in recs if r[5] == t), bytes=sum(r[3] for r in recs if r[5] == t)) for t in tags}
     return out
 
 
