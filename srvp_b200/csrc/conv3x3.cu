@@ -60,6 +60,35 @@ struct ConvDev {
   uint16_t tap_mask[SRVP_CONV_MAX_STAGES];
 };
 
+// Position of a virtual pixel as (frame, y, x); f < 0 marks "before the tensor" (halo rows of the very first tile). Advancing by a
+// constant number of virtual pixels needs no division.
+struct VRow {
+  int f, y, x;
+};
+__device__ __forceinline__ void vrow_init(VRow& rw, long long v, int HpWp, int Wp) {
+  if (v < 0) {
+    const long long vv = v + (long long)HpWp;   // shift by one virtual frame and keep advancing consistently
+    rw.f = -1;
+    rw.y = (int)(vv / Wp);
+    rw.x = (int)(vv - (long long)rw.y * Wp);
+  } else {
+    const unsigned u = (unsigned)v;
+    rw.f = (int)(u / (unsigned)HpWp);
+    const unsigned rem = u - (unsigned)rw.f * (unsigned)HpWp;
+    rw.y = (int)(rem / (unsigned)Wp);
+    rw.x = (int)(rem - (unsigned)rw.y * (unsigned)Wp);
+  }
+}
+__device__ __forceinline__ void vrow_advance(VRow& rw, int df, int dy, int dx, int Hp, int Wp) {
+  rw.x += dx;
+  const int cx = rw.x >= Wp;
+  rw.x -= cx * Wp;
+  rw.y += dy + cx;
+  const int cy = rw.y >= Hp;
+  rw.y -= cy * Hp;
+  rw.f += df + cy;
+}
+
 // Column sums across the 32 lanes of a warp by recursive halving: lane l ends up with sum over lanes of v[l].
 // 31 shuffles for 32 columns (a plain butterfly per column would need 160).
 __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
@@ -151,137 +180,93 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         mbar_wait(&halo_empty[hs], ((it / kHaloStages) & 1) ^ 1);
         uint8_t* hbuf = halo + (size_t)hs * KCH * P * 16;
         if (sd.mode != SRVP_SRC_POOL2) {
-          // One-to-one sources (DIRECT / UP2): every row this thread owns is fetched with asynchronous 16-byte copies straight into
-          // its place in the halo tile (all of them in flight at once, zero-filled for pad pixels), then transformed in place
-          // (BN scale/shift + LeakyReLU) once they have landed. The register-staged version exposed one DRAM latency per row.
-          constexpr int MAXR = 3;   // rows per thread: P <= MAXR * kLoaders (checked on the host)
+          // One-to-one sources (DIRECT / UP2). A thread owns ONE 8-channel chunk (j) of every RSTEP-th row: the KCH lanes that share a
+          // row read / write 16*KCH contiguous bytes of global memory (coalesced source reads and a_out stores), and the chunk's BN
+          // scale / shift live in registers for the whole stage. Phase 1 issues all copies (cp.async straight into the halo tile,
+          // zero-filled for pad pixels), phase 2 walks the same rows again and applies BN + LeakyReLU in place.
+          constexpr int RSTEP = kLoaders / KCH;
+          const int j = lt % KCH, r0 = lt / KCH;
           const int rp = sd.row_pitch ? sd.row_pitch : p.W;
-          int pix[MAXR];            // output pixel index of a valid row (for a_out), -1 = pad row
-#pragma unroll
-          for (int k = 0; k < MAXR; ++k) {
-            const int r = lt + k * kLoaders;
-            pix[k] = -1;
-            if (r < P) {
-              const long long vin = vbase + r;
-              bool valid = vin >= 0 && vin < p.vtotal;
-              int f = 0, y = 0, x = 0;
-              if (valid) {
-                const unsigned v = (unsigned)vin;
-                f = (int)(v / (unsigned)HpWp);
-                const unsigned rem = v - (unsigned)f * (unsigned)HpWp;
-                y = (int)(rem / (unsigned)p.Wp);
-                x = (int)(rem - (unsigned)y * (unsigned)p.Wp);
-                valid = (y < p.H) && (x < p.W);
-              }
+          VRow row0;
+          vrow_init(row0, vbase + r0, HpWp, p.Wp);
+          const int adv_f = RSTEP / HpWp, adv_y = (RSTEP % HpWp) / p.Wp, adv_x = (RSTEP % HpWp) % p.Wp;
+          uint32_t vmask = 0;   // validity of this thread's rows (P / RSTEP <= 32 rows, checked on the host)
+          {
+            VRow rw = row0;
+            int i = 0;
+            for (int r = r0; r < P; r += RSTEP, ++i) {
+              const bool valid = rw.f >= 0 && rw.f < p.F && rw.y < p.H && rw.x < p.W;
               const __nv_bfloat16* src = sd.ptr;
               if (valid) {
-                const int fs = sd.frame_map ? __ldg(sd.frame_map + f) : f;
-                if (sd.mode == SRVP_SRC_UP2) src = sd.ptr + (((size_t)fs * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * sd.cpitch + sd.coff + cloc;
-                else src = sd.ptr + (((size_t)fs * p.H + y) * rp + x) * sd.cpitch + sd.coff + cloc;
-                pix[k] = (f * p.H + y) * p.W + x;
+                const int fs = sd.frame_map ? __ldg(sd.frame_map + rw.f) : rw.f;
+                if (sd.mode == SRVP_SRC_UP2) src = sd.ptr + (((size_t)fs * (p.H >> 1) + (rw.y >> 1)) * (p.W >> 1) + (rw.x >> 1)) * sd.cpitch + sd.coff + cloc + j * 8;
+                else src = sd.ptr + (((size_t)fs * p.H + rw.y) * rp + rw.x) * sd.cpitch + sd.coff + cloc + j * 8;
+                vmask |= 1u << i;
               }
-              const uint32_t nbytes = valid ? 16u : 0u;
-              const int step = valid ? 8 : 0;
-#pragma unroll
-              if (!(p.dbg & 1))
-#pragma unroll
-                for (int j = 0; j < KCH; ++j) cp_async16(hbuf + ((size_t)j * P + r) * 16, src + j * step, nbytes);
+              if (!(p.dbg & 1)) cp_async16(hbuf + ((size_t)j * P + r) * 16, src, valid ? 16u : 0u);
+              vrow_advance(rw, adv_f, adv_y, adv_x, p.Hp, p.Wp);
             }
           }
           cp_async_wait_all();
-          const float* sc = sd.scale ? sd.scale + cloc : nullptr;
-          const float* sh = sd.shift ? sd.shift + cloc : nullptr;
-          if (sc != nullptr || sd.lrelu || store_a) {
-            if constexpr (MT >= 512) {
-              // 2-3 rows per thread: chunk-major, the 8 channels' scale / shift are loaded once and reused over this thread's rows
-#pragma unroll 2
-              for (int j = 0; j < KCH; ++j) {
-                const Affine8 af = load_affine8(sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr);
-#pragma unroll
-                for (int k = 0; k < MAXR; ++k) {
-                  const int r = lt + k * kLoaders;
-                  if (pix[k] < 0) continue;   // pad rows stay zero
-                  uint4* slot = reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16);
-                  const uint4 a = transform8r(*slot, af, sd.lrelu);
-                  if (af.on || sd.lrelu) *slot = a;
-                  if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
-                    *reinterpret_cast<uint4*>(p.a_out + (size_t)pix[k] * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
-                }
+          const bool has_affine = sd.scale != nullptr;
+          if (has_affine || sd.lrelu || store_a) {
+            const Affine8 af = load_affine8(has_affine ? sd.scale + cloc + j * 8 : nullptr, has_affine ? sd.shift + cloc + j * 8 : nullptr);
+            VRow rw = row0;
+            int i = 0;
+#pragma unroll 4
+            for (int r = r0; r < P; r += RSTEP, ++i) {
+              if ((vmask >> i) & 1u) {   // pad rows stay zero
+                uint4* slot = reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16);
+                const uint4 a = transform8r(*slot, af, sd.lrelu);
+                if (has_affine || sd.lrelu) *slot = a;
+                if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
+                  *reinterpret_cast<uint4*>(p.a_out + (size_t)((rw.f * p.H + rw.y) * p.W + rw.x) * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
               }
-            } else {
-              // 1-2 rows per thread: row-major with all 8 chunks of a row unrolled (more loads of the constants, all independent)
-#pragma unroll
-              for (int k = 0; k < MAXR; ++k) {
-                const int r = lt + k * kLoaders;
-                if (pix[k] < 0) continue;   // pad rows stay zero
-                const bool own = store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT;
-                __nv_bfloat16* adst = p.a_out + (size_t)pix[k] * p.a_out_cpitch + s * KCH * 8;
-#pragma unroll
-                for (int j = 0; j < KCH; ++j) {
-                  uint4* slot = reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16);
-                  const uint4 a = transform8(*slot, sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr, sd.lrelu);
-                  if (sc != nullptr || sd.lrelu) *slot = a;
-                  if (own) *reinterpret_cast<uint4*>(adst + j * 8) = a;
-                }
-              }
+              vrow_advance(rw, adv_f, adv_y, adv_x, p.Hp, p.Wp);
             }
           }
         } else {
-          // 2x2 max-pooled source: four raw loads per output chunk, one transform (pool_transform8r); chunk-major as above
-          constexpr int MAXR = 3;
+          // 2x2 max-pooled source, same chunk-owner mapping: four raw loads per output chunk (two rows in flight per thread), ONE
+          // transform (pool_transform8r: per-channel min/max then BN + LeakyReLU), constants in registers for the whole stage
+          constexpr int RSTEP = kLoaders / KCH;
+          constexpr int UR = 2;
+          const int j = lt % KCH, r0 = lt / KCH;
           const int Ws = p.W * 2;
-          const __nv_bfloat16* base[MAXR];
-          int pix[MAXR];
+          const Affine8 af = load_affine8(sd.scale ? sd.scale + cloc + j * 8 : nullptr, sd.scale ? sd.shift + cloc + j * 8 : nullptr);
+          VRow rw;
+          vrow_init(rw, vbase + r0, HpWp, p.Wp);
+          const int adv_f = RSTEP / HpWp, adv_y = (RSTEP % HpWp) / p.Wp, adv_x = (RSTEP % HpWp) % p.Wp;
+          for (int rb = r0; rb < P; rb += UR * RSTEP) {
+            uint4 raw[UR][4];
+            int pix[UR];
 #pragma unroll
-          for (int k = 0; k < MAXR; ++k) {
-            const int r = lt + k * kLoaders;
-            pix[k] = -1;
-            base[k] = sd.ptr;
-            if (r < P) {
-              const long long vin = vbase + r;
-              bool valid = vin >= 0 && vin < p.vtotal;
-              int f = 0, y = 0, x = 0;
-              if (valid) {
-                const unsigned v = (unsigned)vin;
-                f = (int)(v / (unsigned)HpWp);
-                const unsigned rem = v - (unsigned)f * (unsigned)HpWp;
-                y = (int)(rem / (unsigned)p.Wp);
-                x = (int)(rem - (unsigned)y * (unsigned)p.Wp);
-                valid = (y < p.H) && (x < p.W);
-              }
-              if (valid) {
-                const int fs = sd.frame_map ? __ldg(sd.frame_map + f) : f;
-                base[k] = sd.ptr + (((size_t)fs * (p.H * 2) + 2 * y) * Ws + 2 * x) * sd.cpitch + sd.coff + cloc;
-                pix[k] = (f * p.H + y) * p.W + x;
-              } else {
-#pragma unroll
-                for (int j = 0; j < KCH; ++j) *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < UR; ++u) {
+              const int r = rb + u * RSTEP;
+              pix[u] = -2;                                  // -2: row beyond the tile, -1: pad row (zero), >= 0: output pixel
+              if (r < P) {
+                const bool valid = rw.f >= 0 && rw.f < p.F && rw.y < p.H && rw.x < p.W;
+                pix[u] = -1;
+                if (valid) {
+                  const int fs = sd.frame_map ? __ldg(sd.frame_map + rw.f) : rw.f;
+                  const __nv_bfloat16* b = sd.ptr + (((size_t)fs * (p.H * 2) + 2 * rw.y) * Ws + 2 * rw.x) * sd.cpitch + sd.coff + cloc + j * 8;
+                  raw[u][0] = __ldg(reinterpret_cast<const uint4*>(b));
+                  raw[u][1] = __ldg(reinterpret_cast<const uint4*>(b + sd.cpitch));
+                  raw[u][2] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)Ws * sd.cpitch));
+                  raw[u][3] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(Ws + 1) * sd.cpitch));
+                  pix[u] = (rw.f * p.H + rw.y) * p.W + rw.x;
+                }
+                vrow_advance(rw, adv_f, adv_y, adv_x, p.Hp, p.Wp);
               }
             }
-          }
-          const float* sc = sd.scale ? sd.scale + cloc : nullptr;
-          const float* sh = sd.shift ? sd.shift + cloc : nullptr;
-#pragma unroll 2
-          for (int j = 0; j < KCH; ++j) {
-            const Affine8 af = load_affine8(sc ? sc + j * 8 : nullptr, sh ? sh + j * 8 : nullptr);
-            uint4 raw[MAXR][4];
 #pragma unroll
-            for (int k = 0; k < MAXR; ++k) {
-              if (pix[k] < 0) continue;
-              const __nv_bfloat16* b = base[k] + j * 8;
-              raw[k][0] = __ldg(reinterpret_cast<const uint4*>(b));
-              raw[k][1] = __ldg(reinterpret_cast<const uint4*>(b + sd.cpitch));
-              raw[k][2] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)Ws * sd.cpitch));
-              raw[k][3] = __ldg(reinterpret_cast<const uint4*>(b + (size_t)(Ws + 1) * sd.cpitch));
-            }
-#pragma unroll
-            for (int k = 0; k < MAXR; ++k) {
-              if (pix[k] < 0) continue;
-              const int r = lt + k * kLoaders;
-              const uint4 a = pool_transform8r(raw[k][0], raw[k][1], raw[k][2], raw[k][3], af, sd.lrelu);
+            for (int u = 0; u < UR; ++u) {
+              const int r = rb + u * RSTEP;
+              if (pix[u] == -2) continue;
+              uint4 a = make_uint4(0, 0, 0, 0);
+              if (pix[u] >= 0) a = pool_transform8r(raw[u][0], raw[u][1], raw[u][2], raw[u][3], af, sd.lrelu);
               *reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16) = a;
-              if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
-                *reinterpret_cast<uint4*>(p.a_out + (size_t)pix[k] * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
+              if (pix[u] >= 0 && store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
+                *reinterpret_cast<uint4*>(p.a_out + (size_t)pix[u] * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
             }
           }
         }
@@ -674,7 +659,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.num_nblk = a->cout_padded / ch.NB;
   d.num_mtiles = (int)((d.vtotal + ch.MT - 1) / ch.MT);
   d.P = ch.MT + 2 * d.Wp + 2;
-  SRVP_REQUIRE(d.P <= 3 * kLoaders, "conv3x3: halo tile of %d rows exceeds the loader's 3 rows per thread (W=%d)", d.P, a->W);
+  SRVP_REQUIRE(d.P <= 3 * kLoaders && d.P <= 32 * (kLoaders / 8), "conv3x3: halo tile of %d rows exceeds the loader's row budget (W=%d)", d.P, a->W);
   d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   d.out_cpitch = a->out_cpitch; d.out_coff = a->out_coff;
   d.stats_partial = a->stats_partial;
