@@ -658,7 +658,8 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.cout = a->cout;
   d.num_nblk = a->cout_padded / ch.NB;
   d.num_mtiles = (int)((d.vtotal + ch.MT - 1) / ch.MT);
-  d.P = ch.MT + 2 * d.Wp + 2;
+  d.P = (ch.MT + 2 * d.Wp + 2) | 1;   // odd row count: the chunk-plane stride P*16 B is an odd multiple of 16 B, so the 8 lanes that
+                                       // handle the 8 chunks of one pixel row (copy, in-place transform) hit 8 different bank groups
   SRVP_REQUIRE(d.P <= 3 * kLoaders && d.P <= 32 * (kLoaders / 8), "conv3x3: halo tile of %d rows exceeds the loader's row budget (W=%d)", d.P, a->W);
   d.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   d.out_cpitch = a->out_cpitch; d.out_coff = a->out_coff;
