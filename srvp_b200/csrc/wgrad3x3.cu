@@ -293,7 +293,10 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   d.dbg = a->flip >> 8;
   // which operand fills the 128-wide M side
   const int cout_real = a->cout, cin_real = a->cin;
-  d.halo_on_m = (a->dz_channels < 128 && ctot >= 128) ? 1 : 0;
+  // thin dz (the decoder's last layer: 16 padded output channels): activations on M as well, so that dz is the (N = 16) block and ONE CTA
+  // keeps all nine taps -- with dz on M the 64 activation channels form an N = 64 block whose taps are split over two CTAs, which doubles
+  // the L2 -> SM stream of the operand staged with the halo for no gain in MMA count
+  d.halo_on_m = ((a->dz_channels < 128 && ctot >= 128) || (a->dz_channels <= 16 && ctot >= 64)) ? 1 : 0;
   int m_ch, n_ch;
   if (d.halo_on_m) {
     m_ch = ctot; n_ch = a->dz_channels; d.m_real = cin_real; d.n_real = cout_real;
