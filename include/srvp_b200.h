@@ -221,6 +221,26 @@ int srvp_sigmoid_bwd_nchw_to_s2d16(const float* dxhat, const float* xhat, srvp_b
                                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Synchronised batch-norm statistics over NVLink peer memory (reference: SyncBatchNorm, train.py:278-283): the finalisation kernels
+ * above with the cross-rank exchange INSIDE the kernel. Every rank allocates one buffer of srvp_peer_bn_buffer_bytes() with
+ * srvp_peer_alloc (cudaMalloc + IPC handle), exchanges the 64-byte handles out of band (torch.distributed all_gather) and maps the
+ * peers' buffers with srvp_peer_open. `peer_bufs_host` is a HOST array of `world` device pointers (own buffer at index `rank`);
+ * `seq` is a call counter (1, 2, 3, ... identical on all ranks: the calls happen in the same order everywhere). The kernel reduces
+ * the local partial rows, publishes the 2C sums + a flag (release.sys), reads every rank's sums in rank order once their flags
+ * show `seq` (acquire.sys; bounded wait) and finalises with count = count_local * world. Replaces one NCCL all-reduce launch
+ * (~30-40 us, latency bound) per BN layer and direction by ~2 NVLink round trips inside an existing launch.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t srvp_peer_bn_buffer_bytes(void);
+int srvp_peer_alloc(int64_t bytes, void** ptr, uint8_t handle_out[64]);
+int srvp_peer_open(const uint8_t handle[64], void** ptr);
+int srvp_peer_close(void* ptr, int32_t opened);
+int srvp_bn_finalize_p2p(const float* partial, int32_t rows, int32_t C, double count_local, void* const* peer_bufs_host, int32_t rank,
+                         int32_t world, uint64_t seq, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                         float* running_var, float* scale, float* shift, float* mean, float* invstd, void* stream);
+int srvp_bn_bwd_finalize_p2p(const float* partial, int32_t rows, int32_t C, double count_local, void* const* peer_bufs_host, int32_t rank,
+                             int32_t world, uint64_t seq, float* c1, float* c2, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Dense GEMM on tcgen05: C[m,n] (+)= act(sum_k A[m,k]*B[n,k] + bias). Element strides; each operand needs one unit stride.
  * Replaces nn.Linear (module/srvp.py:127-133, mlp.py:43), encoder.last_conv / decoder.first_upconv (conv.py:224, :330)
  * and their gradients.

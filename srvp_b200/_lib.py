@@ -101,6 +101,7 @@ def lib():
         _lib.srvp_last_error.restype = ctypes.c_char_p
         _lib.srvp_launch_count.restype = ctypes.c_uint64
         _lib.srvp_pack_linear_size.restype = ctypes.c_int64
+        _lib.srvp_peer_bn_buffer_bytes.restype = ctypes.c_int64
         for name in EXPORTS:
             getattr(_lib, name)  # AttributeError if the header and the library disagree
     return _lib
@@ -116,6 +117,7 @@ EXPORTS = [
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
     'srvp_bn_tanh_rows_bwd_apply',
     'srvp_u8_to_nhwc_bf16', 'srvp_u8_to_tbchw_f32', 'srvp_rsample_fwd', 'srvp_rsample_bwd', 'srvp_adam_chunk', 'srvp_adam_multi',
+    'srvp_peer_bn_buffer_bytes', 'srvp_peer_alloc', 'srvp_peer_open', 'srvp_peer_close', 'srvp_bn_finalize_p2p', 'srvp_bn_bwd_finalize_p2p',
     'srvp_nll_fwd', 'srvp_nll_bwd', 'srvp_kl_normal_fwd', 'srvp_l2_rows_fwd', 'srvp_scale_by_scalar_f32',
     'srvp_linear_f32', 'srvp_act_bwd_f32', 'srvp_lstm_fwd', 'srvp_lstm_bwd',
     'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum',

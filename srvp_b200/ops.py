@@ -366,13 +366,22 @@ def is_sync_bn(bn):
 @profiled('bn_finalize')
 def bn_finalize(partial, count, bn, state, training_update=True, eps=1e-5, momentum=0.1):
     """partial: (rows, C, 2). bn: torch.nn.BatchNorm2d parameter container (weight, bias, running_*)."""
+    rm = bn.running_mean if training_update else None
+    rv = bn.running_var if training_update else None
     if is_sync_bn(bn):
         from . import parallel
+        peer = parallel.PeerBN.get()
+        if peer is not None and partial.shape[1] <= 1024:
+            # local reduction + exchange over NVLink peer memory + finalisation in one kernel (csrc/peer_bn.cu)
+            state.count = float(count) * peer.world
+            check(lib().srvp_bn_finalize_p2p(ptr(partial), c_int(partial.shape[0]), c_int(partial.shape[1]), ctypes.c_double(count), peer.ptrs,
+                                            c_int(peer.rank), c_int(peer.world), peer.next_seq(), ptr(bn.weight), ptr(bn.bias),
+                                            ctypes.c_float(eps), ctypes.c_float(momentum), ptr(rm), ptr(rv), ptr(state.scale), ptr(state.shift),
+                                            ptr(state.mean), ptr(state.invstd), stream_ptr()), 'bn_finalize_p2p')
+            return state
         partial, count = parallel.allreduce_bn_partial(partial, count)
     state.count = float(count)
     rows, C = partial.shape[0], partial.shape[1]
-    rm = bn.running_mean if training_update else None
-    rv = bn.running_var if training_update else None
     check(lib().srvp_bn_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(bn.weight), ptr(bn.bias),
                                 ctypes.c_float(eps), ctypes.c_float(momentum), ptr(rm), ptr(rv), ptr(state.scale), ptr(state.shift),
                                 ptr(state.mean), ptr(state.invstd), stream_ptr()), 'bn_finalize')
@@ -397,6 +406,24 @@ def channel_stats(z2d):
     return partial
 
 
+def sync_bwd_finalize(partial, rows, C, count, c12, dgamma, dbeta):
+    """SyncBatchNorm backward finalisation: dgamma / dbeta from the LOCAL sums, c1 / c2 from the GLOBAL ones -- fused peer-memory
+    exchange when available (csrc/peer_bn.cu), else local finalise + NCCL all-reduce + global finalise."""
+    from . import parallel
+    peer = parallel.PeerBN.get()
+    if peer is not None and C <= 1024:
+        check(lib().srvp_bn_bwd_finalize_p2p(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), peer.ptrs, c_int(peer.rank),
+                                            c_int(peer.world), peer.next_seq(), ptr(c12[0]), ptr(c12[1]), ptr(dgamma), ptr(dbeta), stream_ptr()),
+              'bn_bwd_finalize_p2p')
+        return
+    scratch = torch.empty(2, C, dtype=torch.float32, device=partial.device)
+    check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(scratch[0]), ptr(scratch[1]),
+                                    ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
+    tot, gcount = parallel.allreduce_bn_partial(partial, count)
+    check(lib().srvp_bn_bwd_finalize(ptr(tot), c_int(1), c_int(C), ctypes.c_double(gcount), ptr(c12[0]), ptr(c12[1]),
+                                    ptr(None), ptr(None), stream_ptr()), 'bn_bwd_finalize')
+
+
 @profiled('bn_bwd')
 def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_coff=0, skip=None, skip_coff=0, nt=0, B=0,
            inv_map=None, lrelu=True, sync=False, g_s2d=False):
@@ -418,13 +445,7 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     count = float(frames * H * W)
     if sync:
         # SyncBatchNorm backward: dgamma / dbeta from the LOCAL sums (DDP averages them), the dx correction from the GLOBAL sums
-        from . import parallel
-        scratch = torch.empty(2, C, dtype=torch.float32, device=dev)
-        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(scratch[0]), ptr(scratch[1]),
-                                        ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
-        tot, gcount = parallel.allreduce_bn_partial(partial, count)
-        check(lib().srvp_bn_bwd_finalize(ptr(tot), c_int(1), c_int(C), ctypes.c_double(gcount), ptr(c12[0]), ptr(c12[1]),
-                                        ptr(None), ptr(None), stream_ptr()), 'bn_bwd_finalize')
+        sync_bwd_finalize(partial, rows, C, count, c12, dgamma, dbeta)
     else:
         check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(c12[0]), ptr(c12[1]),
                                         ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
@@ -554,12 +575,8 @@ def bn_tanh_rows_bwd(dout, out, z, gamma, state, dgamma, dbeta, sync=False):
         partial = torch.empty(1, C, 2, dtype=torch.float32, device=dev)
         check(lib().srvp_bn_tanh_rows_bwd_reduce(ptr(dout), ptr(out), ptr(z), c_int(rows), c_int(C), ptr(state.mean), ptr(state.invstd),
                                                 ptr(partial), stream_ptr()), 'bn_tanh_rows_bwd_reduce')
-        c12, scratch = torch.empty(2, C, dtype=torch.float32, device=dev), torch.empty(2, C, dtype=torch.float32, device=dev)
-        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(1), c_int(C), ctypes.c_double(float(rows)), ptr(scratch[0]), ptr(scratch[1]),
-                                        ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
-        tot, gcount = parallel.allreduce_bn_partial(partial, float(rows))
-        check(lib().srvp_bn_bwd_finalize(ptr(tot), c_int(1), c_int(C), ctypes.c_double(gcount), ptr(c12[0]), ptr(c12[1]), ptr(None), ptr(None),
-                                        stream_ptr()), 'bn_bwd_finalize')
+        c12 = torch.empty(2, C, dtype=torch.float32, device=dev)
+        sync_bwd_finalize(partial, 1, C, float(rows), c12, dgamma, dbeta)
         check(lib().srvp_bn_tanh_rows_bwd_apply(ptr(dout), ptr(out), ptr(z), c_int(rows), c_int(C), ptr(gamma), ptr(state.mean),
                                                ptr(state.invstd), ptr(c12[0]), ptr(c12[1]), ptr(dz), stream_ptr()), 'bn_tanh_rows_bwd_apply')
         return dz
