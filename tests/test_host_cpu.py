@@ -116,3 +116,84 @@ def test_two_rank_plumbing_on_gloo():
     for r in res:
         assert r[3] == [1.5] * 3 and r[4] == [15.0] * 4
         assert r[5] == [3.0, 5.0] and r[6] == 11.0
+
+
+def test_dcgan_class_surface_and_no_cpu_fallback():
+    """DCGAN64 containers: state-dict contract of SURVEY.md App. E and the same refusal to run without CUDA."""
+    cfg = dict(nx=64, nc=1, nf=64, nhx=128, ny=20, nz=20, skipco=False, nt_inf=5, nh_inf=256, nlayers_inf=3, nh_res=512, nlayers_res=4,
+               archi='dcgan')
+    m = build_model(cfg, 1.41, 0)
+    assert sum(p.numel() for p in m.parameters()) == 10678284 and len(m.state_dict()) == 82
+    keys = set(m.state_dict().keys())
+    for k in ['encoder.conv.0.0.weight', 'encoder.conv.3.1.running_var', 'encoder.last_conv.0.weight', 'decoder.first_upconv.0.weight',
+              'decoder.conv.2.1.bias', 'decoder.conv.3.weight', 'inf_z.weight_hh_l0', 'q_y.module.2.1.weight']:
+        assert k in keys, k
+    assert tuple(m.state_dict()['decoder.conv.3.weight'].shape) == (64, 1, 4, 4)
+    with pytest.raises(RuntimeError):
+        m.encoder(torch.rand(2, 1, 64, 64))
+    with pytest.raises((RuntimeError, AssertionError)):
+        m(torch.rand(3, 2, 1, 64, 64), 3, dt=1.0)
+
+
+def test_4x4_stride2_tap_tables_match_the_convolution_arithmetic():
+    """Host functions of the 4x4 stride-2 family: the tap masks the library hands to the kernels are exactly the (phase, tap) pairs for
+    which a 4x4 / stride 2 / pad 1 (transposed) convolution has a weight, and using ONLY those pairs reproduces F.conv2d /
+    F.conv_transpose2d (the space-to-depth restatement of include/srvp_b200.h, checked here in fp32 on the CPU)."""
+    import torch.nn.functional as F
+    from srvp_b200 import _lib, ops
+    down = lambda py, ty: 2 * ty + py - 1
+    up = lambda py, ty: py + 3 - 2 * ty
+    for kind, f in ((_lib.W4_DOWN, down), (_lib.W4_UP_PHASE, up)):
+        for py in range(2):
+            for px in range(2):
+                want = sum(1 << (ty * 3 + tx) for ty in range(3) for tx in range(3) if 0 <= f(py, ty) < 4 and 0 <= f(px, tx) < 4)
+                assert ops.tap_mask4(kind, py, px) == want and bin(want).count('1') == 4
+    g = torch.Generator().manual_seed(0)
+    C, Co, H = 3, 5, 8
+    x, w, wt = torch.randn(2, C, H, H, generator=g), torch.randn(Co, C, 4, 4, generator=g), torch.randn(C, Co, 4, 4, generator=g)
+    xs = torch.cat([x[:, :, py::2, px::2] for py in range(2) for px in range(2)], 1)
+    w3 = torch.zeros(Co, 4 * C, 3, 3)
+    for ph in range(4):
+        m = ops.tap_mask4(_lib.W4_DOWN, ph >> 1, ph & 1)
+        for tap in range(9):
+            if m >> tap & 1:
+                w3[:, ph * C:(ph + 1) * C, tap // 3, tap % 3] = w[:, :, down(ph >> 1, tap // 3), down(ph & 1, tap % 3)]
+    assert torch.allclose(F.conv2d(xs, w3, None, 1, 1), F.conv2d(x, w, None, 2, 1), atol=1e-5)
+    out = torch.zeros(2, Co, 2 * H, 2 * H)
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        m = ops.tap_mask4(_lib.W4_UP_PHASE, py, px)
+        w3 = torch.zeros(Co, C, 3, 3)
+        for tap in range(9):
+            if m >> tap & 1:
+                w3[:, :, tap // 3, tap % 3] = wt[:, :, up(py, tap // 3), up(px, tap % 3)].t()
+        out[:, :, py::2, px::2] = F.conv2d(x, w3, None, 1, 1)
+    assert torch.allclose(out, F.conv_transpose2d(x, wt, None, 2, 1), atol=1e-5)
+
+
+def test_host_side_sizing_functions():
+    """Grid / buffer sizing entry points are pure host code: consistent with what the wrappers allocate."""
+    from srvp_b200 import _lib
+    lib = _lib.lib()
+    c_int = _lib.c_int
+    # statistics rows = persistent grid size, never more than the tile count
+    assert lib.srvp_conv3x3_num_mtiles(c_int(1), c_int(8), c_int(8), c_int(64), c_int(64)) == 1
+    big = lib.srvp_conv3x3_num_mtiles(c_int(2304), c_int(64), c_int(64), c_int(64), c_int(64))
+    assert 1 < big <= 1024 and big == lib.srvp_num_sms()
+    assert lib.srvp_conv3x3_nblock(c_int(16)) == 16 and lib.srvp_conv3x3_nblock(c_int(512)) == 256
+    rows = lib.srvp_bn_bwd_reduce_rows(c_int(2304), c_int(64), c_int(64), c_int(64), c_int(0))
+    assert 1 <= rows <= 2048 and rows * 64 <= (1 << 20)
+    assert lib.srvp_bn_bwd_reduce_rows(c_int(1), c_int(4), c_int(4), c_int(512), c_int(0)) == 1
+    assert lib.srvp_adam_chunk() > 0 and lib.srvp_peer_bn_buffer_bytes() > 2 * 1024 * 16
+    assert lib.srvp_pack_linear_size(c_int(512), c_int(100)) >= 512 * 100
+
+
+def test_peer_bn_exchange_is_gated():
+    """The peer-memory SyncBatchNorm exchange is opt-in and never used without an NCCL process group."""
+    from srvp_b200 import parallel
+    assert parallel.PeerBN.get() is None
+    os.environ['SRVP_BN_P2P'] = '1'
+    try:
+        assert parallel.PeerBN.get() is None      # no process group here
+    finally:
+        del os.environ['SRVP_BN_P2P']
