@@ -5,9 +5,10 @@
 // them is a latency-bound all-reduce launch (~30-40 us at 8 ranks) on the critical path between two convolutions. Here every rank owns a
 // small buffer that all peers map (cudaIpc over NVLink / NVSwitch); the finalisation kernel
 //   1. reduces its own per-CTA partial rows (fp64),
-//   2. publishes the 2C sums in its buffer and raises a per-block flag (release, system scope),
-//   3. reads the sums of every rank in rank order through the peer mappings as soon as their flags show this call's sequence
-//      number (acquire) -- the same fixed order on every rank, so all ranks compute bit-identical statistics,
+//   2. PUSHES the 2C sums into its mailbox inside EVERY peer's buffer (posted NVLink writes) and then raises its per-block flag there
+//      (release, system scope) -- remote READS of a busy peer cost tens of microseconds each, remote writes are fire-and-forget,
+//   3. polls its OWN buffer (local memory) until the mailbox of every rank shows this call's sequence number (acquire) and adds the
+//      sums in rank order -- the same fixed order on every rank, so all ranks compute bit-identical statistics,
 //   4. finalises (scale / shift / saved statistics / running statistics, or c1 / c2 / dgamma / dbeta).
 // Two slots alternate between consecutive calls: a rank can only be one call ahead of the slowest peer (it needs that peer's flag of
 // the previous call), so slot (seq & 1) is never overwritten while a peer still reads it. Waits are bounded (trap after ~2 s).
@@ -21,9 +22,12 @@ constexpr int kMaxRanks = 16;
 constexpr int kMaxC = 1024;
 constexpr int kBlocks = kMaxC / 32;
 
-struct PeerSlot {
-  unsigned long long flag[kBlocks];   // sequence number of the last call whose sums of channel block b are complete
+struct Mailbox {
+  unsigned long long flag[kBlocks];   // sequence number of the last call whose sums of channel block b have arrived from this source rank
   double sums[kMaxC][2];
+};
+struct PeerSlot {
+  Mailbox from[kMaxRanks];            // written by rank `src` (remotely), read by the owner (locally)
 };
 struct PeerBuf {
   PeerSlot slot[2];
@@ -69,18 +73,28 @@ __device__ __forceinline__ void exchange(const float* __restrict__ partial, int 
   if (rl != 0) return;
 #pragma unroll
   for (int k = 1; k < 8; ++k) { s1 += r1[k][cl]; s2 += r2[k][cl]; }
-  PeerSlot* mine = &tab.buf[rank]->slot[seq & 1ull];
-  if (c < C) { mine->sums[c][0] = s1; mine->sums[c][1] = s2; }
+  // push: my sums into my mailbox in every peer's buffer, then the flag
+  for (int pr = 0; pr < world; ++pr) {
+    if (pr == rank) continue;
+    Mailbox* box = &tab.buf[pr]->slot[seq & 1ull].from[rank];
+    if (c < C) {
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&box->sums[c][0]), "d"(s1) : "memory");
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&box->sums[c][1]), "d"(s2) : "memory");
+    }
+  }
   __threadfence_system();
   __syncwarp();
-  if (cl == 0) st_release_sys(&mine->flag[blockIdx.x], seq);
+  if (cl == 0)
+    for (int pr = 0; pr < world; ++pr)
+      if (pr != rank) st_release_sys(&tab.buf[pr]->slot[seq & 1ull].from[rank].flag[blockIdx.x], seq);
+  // pull from LOCAL memory, in rank order
+  const PeerSlot* mine = &tab.buf[rank]->slot[seq & 1ull];
   for (int pr = 0; pr < world; ++pr) {
     if (pr == rank) { g1 += s1; g2 += s2; continue; }
-    const PeerSlot* theirs = &tab.buf[pr]->slot[seq & 1ull];
+    const Mailbox* box = &mine->from[pr];
     if (cl == 0) {
       const long long t0 = clock64();
-      while (ld_acquire_sys(&theirs->flag[blockIdx.x]) < seq) {
-        __nanosleep(100);
+      while (ld_acquire_sys(&box->flag[blockIdx.x]) < seq) {
         if (clock64() - t0 > 4000000000LL) {
           printf("srvp: peer batch-norm exchange timed out (rank %d waits for rank %d, block %d, call %llu)\n", rank, pr, (int)blockIdx.x, seq);
           __trap();
@@ -89,7 +103,7 @@ __device__ __forceinline__ void exchange(const float* __restrict__ partial, int 
     }
     __syncwarp();
     __threadfence_system();
-    if (c < C) { g1 += ld_relaxed_sys_f64(&theirs->sums[c][0]); g2 += ld_relaxed_sys_f64(&theirs->sums[c][1]); }
+    if (c < C) { g1 += ld_relaxed_sys_f64(&box->sums[c][0]); g2 += ld_relaxed_sys_f64(&box->sums[c][1]); }
   }
 }
 

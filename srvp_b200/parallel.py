@@ -54,8 +54,9 @@ class PeerBN:
     is not enabled or cannot be used (single process, non-NCCL backend, IPC mapping failed) -- callers then take the NCCL path.
 
     OPT-IN (SRVP_BN_P2P=1) in this round: results are bit-identical across ranks and match the NCCL path (tests/multigpu_check.py at
-    2 GPUs), but the first version is slower than NCCL's small all-reduce (2 GPUs: 73.9 vs 73.2 ms/step, 4 GPUs: 92.7 vs 74.4 ms/step,
-    profiles/r02d_*, r02e_*): the system-scope fences and the flag polling over NVLink cost ~200 us per call at 4 ranks."""
+    2 GPUs); the push-based version (remote writes into the peers' mailboxes, local polling) is at parity with NCCL's small all-reduce
+    (4 GPUs: 75.0 vs 74.4 ms/step, profiles/r02e_*, r02f_*), the first pull-based version (remote flag polling / remote reads of busy
+    peers) cost ~200 us per call (92.7 ms/step)."""
     _inst = None
     _failed = False
 
