@@ -16,6 +16,7 @@
 // all 9 taps' accumulators in TMEM (9 * NBc fp32 columns), looping over its pixel range in steps of 128
 // pixels. Split-K partial results are added into the fp32 gradient with red.global.add.f32.
 // Either operand can sit on the M side (`halo_on_m`), so that layers with 64 output channels still fill M.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/srvp_b200.h"
 
@@ -314,7 +315,9 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   d.num_nblk = n_ch / NBc;
   const int sms = num_sms_cached();
   const int pairs = d.num_mblk * d.num_nblk * d.tap_groups;
-  int splits = (2 * sms) / pairs;  // ~2 waves worth of CTAs keeps the tail short; each CTA is resident alone
+  static int waves = 0;            // CTAs per SM over the launch (development override: SRVP_WGRAD_WAVES)
+  if (waves == 0) { const char* e = getenv("SRVP_WGRAD_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1) waves = 1; }
+  int splits = (waves * sms) / pairs;  // one CTA per SM measured best (1: 23.6, 2: 24.4, 3-4: 24.7 ms/step, profiles/r02g_wgrad_waves.log)
   if (splits < 1) splits = 1;
   if (splits > d.steps_total) splits = d.steps_total;
   d.splits = splits;
