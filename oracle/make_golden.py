@@ -32,6 +32,10 @@ CASES = {
     'dcgan_nc1': dict(cfg=dict(nx=64, nc=1, nf=64, nhx=128, ny=20, nz=20, skipco=False, nt_inf=5, nh_inf=256, nlayers_inf=3,
                                nh_res=512, nlayers_res=4, archi='dcgan'),
                       T=6, B=2, dt=1.0, loss=dict(obs_scale=1.0, beta_y=1.0, beta_z=2.0, l2_res=1.0), res_gain=1.41),
+    # DCGAN with skip connections and colour frames (the `--skipco` flag of the reference with its default architecture)
+    'dcgan_skip_nc3': dict(cfg=dict(nx=64, nc=3, nf=64, nhx=128, ny=20, nz=20, skipco=True, nt_inf=2, nh_inf=256, nlayers_inf=3,
+                                    nh_res=512, nlayers_res=4, archi='dcgan'),
+                           T=5, B=3, dt=0.5, loss=dict(obs_scale=1.0, beta_y=1.0, beta_z=2.0, l2_res=1.0), res_gain=1.41),
 }
 ARG_ORDER = ['nx', 'nc', 'nf', 'nhx', 'ny', 'nz', 'skipco', 'nt_inf', 'nh_inf', 'nlayers_inf', 'nh_res', 'nlayers_res', 'archi']
 SEED_MODEL, SEED_INPUT, SEED_FWD = 1, 123, 7
@@ -174,5 +178,7 @@ def run_case(name, case):
 if __name__ == '__main__':
     torch.set_num_threads(8)
     sys.path.insert(0, REF)
+    only = sys.argv[1:]            # optional: names of the cases to (re)generate
     for name, case in CASES.items():
-        run_case(name, case)
+        if not only or name in only:
+            run_case(name, case)

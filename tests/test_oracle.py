@@ -5,7 +5,7 @@ import torch
 from common import GOLDEN_DIR, build_model, load_golden, make_input
 from oracle import srvp_oracle as O
 
-CASES = ['vgg_skip_nc3', 'vgg_skip_nc1', 'dcgan_nc1']
+CASES = ['vgg_skip_nc3', 'vgg_skip_nc1', 'dcgan_nc1', 'dcgan_skip_nc3']
 
 
 @pytest.fixture(scope='module', params=CASES)
