@@ -99,6 +99,17 @@ def _enc_params(enc):
     return ps
 
 
+def _grad_targets(params):
+    """Per parameter: the tensor the backward kernels accumulate into (ops.grad_target) and whether it already is p.grad."""
+    pairs = [ops.grad_target(p) for p in params]
+    return [t for t, _ in pairs], [d for _, d in pairs]
+
+
+def _returned(grads, direct):
+    """Gradients handed back to autograd: None where the kernels wrote p.grad itself (GradBucket views)."""
+    return [None if d else g for g, d in zip(grads, direct)]
+
+
 def _ensure_plan(m):
     if getattr(m, '_plan', None) is None:
         if m.archi == 'dcgan':
@@ -166,7 +177,7 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
     """Returns the list of parameter gradients in _enc_params order."""
     plan = enc._plan
     F_, dev = c.F, d_hx.device
-    grads = [torch.zeros_like(p) for p in _enc_params(enc)]
+    grads, direct = _grad_targets(_enc_params(enc))
     conv_l, bn_l = _last_block(enc)
     C = conv_l.in_channels
     gi = len(grads) - 3
@@ -175,13 +186,13 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
     # weight gradient: dWl[co, (y,x,c)] = sum_f dz_last[f, co] * a_last[f, (y,x,c)]
     dwl = torch.zeros(enc.nh, 16, C, dtype=torch.float32, device=dev)
     ops.gemm(dz_last.t(), c.a_last.view(F_, 16 * C).t(), dwl.view(enc.nh, 16 * C), accumulate=True)
-    grads[gi] = ops.transpose_last2(dwl).view_as(conv_l.weight)
+    ops.transpose_last2(dwl, out=grads[gi])
     # data gradient w.r.t. the pooled activation: (F, 4, 4, C)
     da = torch.empty(F_, 4, 4, C, dtype=torch.bfloat16, device=dev)
     ops.gemm(dz_last, c.wl.view(enc.nh, 16 * C).t(), da.view(F_, 16 * C))
     if plan == 'dcgan':
         _dcgan_encoder_convs_bwd(enc, c, da, grads, skip_handle)
-        return grads
+        return _returned(grads, direct)
     da_mode = SRC_POOL2
     for li in range(len(plan) - 1, -1, -1):
         blk = plan[li]
@@ -198,7 +209,7 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, blk.cin)
             da_mode = blk.in_mode  # POOL2: the producer is at twice this resolution
-    return grads
+    return _returned(grads, direct)
 
 
 class EncoderFn(torch.autograd.Function):
@@ -338,10 +349,10 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     plan = dec._plan
     F_, dev = c.F, d_xhat.device
     params = _dec_params(dec)
-    grads = [torch.zeros_like(p) for p in params]
+    grads, direct = _grad_targets(params)
     if plan == 'dcgan':
         da = _dcgan_decoder_convs_bwd(dec, c, d_xhat, grads, skip_handle)
-        return _decoder_head_bwd(dec, c, da, SRC_DIRECT, grads)
+        return _decoder_head_bwd(dec, c, da, SRC_DIRECT, grads, direct)
     final = dec.conv[3][1]
     nc = final.out_channels
     dz = ops.sigmoid_bwd(d_xhat.contiguous(), c.x_hat)  # (F,64,64,16)
@@ -380,10 +391,10 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
         da_mode, da_coff = blk.in_mode, 0
     if skip_handle is not None and skip_grads:
         skip_handle.grads = [skip_grads[i] for i in range(len(skip_grads))]
-    return _decoder_head_bwd(dec, c, da, SRC_UP2, grads)
+    return _decoder_head_bwd(dec, c, da, SRC_UP2, grads, direct)
 
 
-def _decoder_head_bwd(dec, c, da, da_mode, grads):
+def _decoder_head_bwd(dec, c, da, da_mode, grads, direct):
     """first_upconv backward: BN/LeakyReLU[/Upsample] backward, then the two GEMMs of the 1x1 -> 4x4 transposed convolution."""
     F_, dev = c.F, da.device
     up_conv, up_bn = _first_block(dec)
@@ -393,8 +404,8 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads):
     ops.gemm(dz0.view(F_, 16 * C0), c.wp0.view(nin, 16 * C0), d_inp, det_split=8 if (16 * C0) % (8 * 64) == 0 else 0)
     dwp = torch.zeros(nin, 16, C0, dtype=torch.float32, device=dev)
     ops.gemm(c.dec_inp.t(), dz0.view(F_, 16 * C0).t(), dwp.view(nin, 16 * C0), accumulate=True)
-    grads[0] = ops.transpose_last2(dwp).view_as(up_conv.weight)
-    return d_inp, grads
+    ops.transpose_last2(dwp, out=grads[0])
+    return d_inp, _returned(grads, direct)
 
 
 class DecoderFn(torch.autograd.Function):
@@ -412,6 +423,9 @@ class DecoderFn(torch.autograd.Function):
         d_inp, grads = _decoder_bwd(ctx.dec, ctx.c, d_xhat, ctx.skip_handle)
         ops.PROFILE_TAG = ''
         ctx.c = None
+        from . import parallel
+        if parallel.ACTIVE_BUCKET is not None:
+            parallel.ACTIVE_BUCKET.segment_ready()     # the decoder's gradients are final: their all-reduce overlaps the rest of backward
         return (None, d_inp, None, None, None, None, *grads)
 
 

@@ -29,6 +29,9 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         self.nh_res, self.nlayers_res = nh_res, nlayers_res
         self.nhx = nhx
         self.noise_device = 'cpu'
+        # Test hook: a dict of explicit random draws {'t_skip', 't_w', 'eps_y', 'eps_z': [...]} (the layout of oracle.draw_randoms,
+        # SURVEY.md App. D) consumed instead of drawing -- lets a sharded run use its slice of the global batch's draws.
+        self.injected_randoms = None
         # construction order = reference order (module/srvp.py:124-137): it fixes the same-seed default initialisation
         self.encoder = conv.encoder_factory(archi, nx, nc, nhx, nf)
         self.decoder = conv.decoder_factory(archi, nx, nc, nh_inf + ny, nf, skipco)
@@ -58,8 +61,11 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
             return self._to_device(torch.empty(shape, dtype=torch.float32).normal_(), like.device)
         return torch.empty(shape, dtype=torch.float32, device=like.device).normal_()
 
-    def _rsample(self, raw_params):
+    def _rsample(self, raw_params, key=None):
         shape = (*raw_params.shape[:-1], raw_params.shape[-1] // 2)
+        inj = self.injected_randoms
+        if inj is not None and key is not None and key in inj:
+            return infer.rsample(raw_params, self._to_device(inj[key].float().reshape(shape), raw_params.device))
         return infer.rsample(raw_params, self._normal(shape, raw_params))
 
     # ------------------------------------------------------------------------------------------------ encode / decode
@@ -69,8 +75,9 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         handle = engine.SkipHandle() if self.skipco else None
         hx = engine.encoder_apply(self.encoder, x.reshape(nt * bsz, *x.shape[2:]), handle).view(nt, bsz, self.nhx)
         if self.skipco:
+            inj = self.injected_randoms
             if self.training:
-                t = torch.randint(nt, size=(bsz,))
+                t = inj['t_skip'].long() if inj is not None and 't_skip' in inj else torch.randint(nt, size=(bsz,))
             else:
                 t = torch.full((bsz,), nt - 1, dtype=torch.long)
             sel = (t * bsz + torch.arange(bsz)).to(torch.int32)          # encoder frame feeding each video's skip
@@ -117,7 +124,9 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         """module/srvp.py:229-256"""
         nt, bsz = hx.shape[0], hx.shape[1]
         if self.training:
-            t = self._to_device(torch.stack([torch.randperm(nt)[:self.nt_inf] for _ in range(bsz)], 1), hx.device)
+            inj = self.injected_randoms
+            t = inj['t_w'].long() if inj is not None and 't_w' in inj else torch.stack([torch.randperm(nt)[:self.nt_inf] for _ in range(bsz)], 1)
+            t = self._to_device(t, hx.device)
             index = torch.arange(bsz, device=hx.device).repeat(self.nt_inf, 1)
             h = hx[t.view(-1), index.view(-1)].view(self.nt_inf, bsz, self.nhx)
         else:
@@ -127,7 +136,7 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
     def infer_y(self, hx):
         """module/srvp.py:258-278"""
         q_y_0_params = infer.mlp(hx.permute(1, 0, 2).reshape(hx.shape[1], self.nt_inf * self.nhx), self.q_y)
-        return self._rsample(q_y_0_params), q_y_0_params
+        return self._rsample(q_y_0_params, 'eps_y'), q_y_0_params
 
     def infer_z(self, hx):
         """module/srvp.py:280-298"""
@@ -153,7 +162,11 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         if n_obs > 0:
             hx_z = infer.lstm(hx, self.inf_z)                # one launch for the whole recurrence (srvp.py:365-368)
         # noise in the reference's order: one (B, nz) draw per generated frame (posterior or prior alike)
-        eps = torch.stack([self._normal((bsz, self.nz), y_0) for _ in range(nt - 1)]) if nt > 1 else None
+        inj = self.injected_randoms
+        if inj is not None and 'eps_z' in inj and nt > 1:
+            eps = self._to_device(torch.stack([e.float() for e in inj['eps_z'][:nt - 1]]), y_0.device)
+        else:
+            eps = torch.stack([self._normal((bsz, self.nz), y_0) for _ in range(nt - 1)]) if nt > 1 else None
         if n_post > 0:
             q_z_params = infer.linear(hx_z[1:n_post + 1], self.q_z)
             z_post = infer.rsample(q_z_params, eps[:n_post])

@@ -23,11 +23,13 @@ def profiled(name):
                 return fn(*args, **kwargs)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _WORK.append([0.0, 0.0, 0.0])
+            _WORK.append([0.0, 0.0, 0.0, None])
             out = fn(*args, **kwargs)
             e1.record()
-            fl, by, fx = _WORK.pop()
+            fl, by, fx, sub = _WORK.pop()
             PROFILE.setdefault(name, []).append((e0, e1, fl, by, fx, PROFILE_TAG))
+            if sub is not None:      # HBM-bound members of a tensor-bound family, also listed by themselves (bench.py hbm_kernels)
+                PROFILE.setdefault(sub, []).append((e0, e1, fl, by, fx, PROFILE_TAG))
             return out
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__
@@ -38,13 +40,15 @@ def profiled(name):
 _WORK = []
 
 
-def _account(flops=0.0, nbytes=0.0, executed=None):
+def _account(flops=0.0, nbytes=0.0, executed=None, sub=None):
     """flops: ALGORITHMIC dense count of the reference op this launch stands for; executed: multiply-adds actually
-    issued when they differ (per-video split of the skip convolutions)."""
+    issued when they differ (per-video split of the skip convolutions); sub: extra profile entry this launch is also listed under."""
     if _WORK:
         _WORK[-1][0] += flops
         _WORK[-1][1] += nbytes
         _WORK[-1][2] += flops if executed is None else executed
+        if sub is not None:
+            _WORK[-1][3] = sub
 
 
 def summarize_profile(profile):
@@ -59,6 +63,16 @@ def summarize_profile(profile):
             out[name]['by_stage'] = {t: dict(launches=sum(1 for r in recs if r[5] == t), ms=sum(r[0].elapsed_time(r[1]) for r in recs if r[5] == t),
                                              flops=sum(r[2] for r in recs if r[5] == t), bytes=sum(r[3] for r in recs if r[5] == t)) for t in tags}
     return out
+
+
+def grad_target(p):
+    """(tensor the backward kernels accumulate the gradient of parameter p into, direct): direct = it IS the parameter's gradient
+    (a zeroed view of parallel.GradBucket's flat buffer attached as p.grad), so nothing is returned to autograd for it; otherwise a
+    fresh zero tensor that autograd receives."""
+    v = getattr(p, '_srvp_sink', None)
+    if v is not None and p.grad is v:
+        return v, True
+    return torch.zeros_like(p), False
 
 
 @dataclass
@@ -190,7 +204,9 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
     a.map4, a.phase_channels = map4, phase_channels
     check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
     fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
-    _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx)
+    # thin operands (first encoder / last decoder layer): HBM-bound, also listed by themselves (bench.py hbm_kernels)
+    sub = f'hbm:wgrad_thin[{PROFILE_TAG}]' if min(dz_channels, act_channels) <= 16 else None
+    _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx, sub=sub)
     return dw
 
 
@@ -256,7 +272,13 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
     obytes = (out.numel() * out.element_size()) if not out_xstride else 2.0 * frames * H * W * cout
     fx = 2.0 * frames * H * W * cout * cin_real * taps
     # alg_scale: algorithmic (reference, dense) FLOPs this launch stands for / executed ones (split skip convolutions: 2 and 0)
-    _account(fx * alg_scale, executed=fx, nbytes= sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes)
+    nbytes = sum(2.0 * frames * H * W * s.channels / (4 if s.mode == _lib.SRC_UP2 else 1) for s in srcs) + obytes
+    sub = None
+    if sigmoid_nchw or (len(srcs) == 1 and srcs[0].channels == 16):
+        # HBM-bound ends of the network: algorithmic bytes = real input channels read once + output written once
+        sub = f'hbm:conv_head_sigmoid[{PROFILE_TAG}]' if sigmoid_nchw else f'hbm:conv_thin_in[{PROFILE_TAG}]'
+        nbytes = 2.0 * frames * H * W * cin_real + obytes
+    _account(fx * alg_scale, executed=fx, nbytes=nbytes, sub=sub)
     if save_input:
         return out, stats_partial, a_out
     return out, stats_partial
@@ -337,10 +359,12 @@ def materialize(src, frames, H, W):
 
 
 @profiled('transpose_last2')
-def transpose_last2(t):
-    """(A, B, C) fp32 -> (A, C, B)."""
+def transpose_last2(t, out=None):
+    """(A, B, C) fp32 -> (A, C, B) (optionally into a contiguous `out` of A*C*B elements)."""
     A, B, C = t.shape
-    out = torch.empty(A, C, B, dtype=torch.float32, device=t.device)
+    if out is None:
+        out = torch.empty(A, C, B, dtype=torch.float32, device=t.device)
+    assert out.numel() == A * B * C and out.is_contiguous()
     check(lib().srvp_transpose_last2_f32(ptr(t), ptr(out), c_int(A), c_int(B), c_int(C), stream_ptr()), 'transpose_last2')
     return out
 

@@ -17,16 +17,18 @@ class Adam(torch.optim.Optimizer):
 
     def _table(self, gi, params):
         """Device table of the group's fixed pointers (param, exp_avg, exp_avg_sq), sizes and block prefix; grads are refreshed per step."""
-        key = (gi, tuple(p.data_ptr() for p in params))
+        for p in params:
+            st = self.state[p]
+            if len(st) == 0:
+                st['step'] = torch.zeros((), dtype=torch.float32)
+                st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        # the cached table holds raw device pointers: it is keyed on the parameters' AND the moments' storage, so that a
+        # load_state_dict() (which replaces the state tensors) or a parameter re-allocation rebuilds it
+        key = (gi, tuple((p.data_ptr(), self.state[p]['exp_avg'].data_ptr(), self.state[p]['exp_avg_sq'].data_ptr()) for p in params))
         if self._tables.get(gi, (None,))[0] != key:
             chunk = lib().srvp_adam_chunk()
             dev = params[0].device
-            for p in params:
-                st = self.state[p]
-                if len(st) == 0:
-                    st['step'] = torch.zeros((), dtype=torch.float32)
-                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
             sizes = [p.numel() for p in params]
             starts, acc = [], 0
             for n in sizes:
@@ -35,6 +37,17 @@ class Adam(torch.optim.Optimizer):
             rows = [[p.data_ptr(), 0, self.state[p]['exp_avg'].data_ptr(), self.state[p]['exp_avg_sq'].data_ptr()] for p in params]
             self._tables[gi] = (key, rows, torch.tensor(sizes, dtype=torch.int64, device=dev), torch.tensor(starts, dtype=torch.int32, device=dev), acc)
         return self._tables[gi]
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}          # the state tensors were replaced: drop every cached pointer table
+        for st in self.state.values():
+            if 'step' in st and torch.is_tensor(st['step']):
+                st['step'] = st['step'].detach().to('cpu', torch.float32)     # the step count lives on the host (bias correction scalars)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -36,6 +36,75 @@ def allreduce_mean_(tensors):
     return tensors
 
 
+class GradBucket:
+    """All parameter gradients of a model as views of ONE flat fp32 buffer (the role of DistributedDataParallel's
+    gradient_as_bucket_view=True bucket, reference train.py:314).
+
+    * zero(): one memset per step instead of one fill per tensor; re-attaches p.grad = view.
+    * The backward kernels of the conv stacks accumulate straight into the views (ops.grad_target): no per-tensor zero fill, no
+      flatten / unflatten copies around the all-reduce.
+    * allreduce_mean(): ONE in-place all-reduce (NCCL AVG over NVLink / NVSwitch; sum + scale on gloo). `early` (a list of
+      parameters, e.g. the decoder's) is laid out first: segment_ready() launches its all-reduce asynchronously as soon as the
+      decoder backward has produced it, overlapping the rest of the backward pass; allreduce_mean() then reduces the remainder and
+      waits for both.
+    """
+
+    def __init__(self, params, early=None):
+        params = list(params)
+        early_ids = {id(p) for p in (early or [])}
+        self.params = [p for p in params if id(p) in early_ids] + [p for p in params if id(p) not in early_ids]
+        assert all(p.dtype == torch.float32 for p in self.params), 'fp32 parameters only'
+        offs, acc = [], 0
+        for p in self.params:
+            offs.append(acc)
+            acc += (p.numel() + 3) // 4 * 4          # 16-byte aligned views (vector loads in the Adam / backward kernels)
+        self.n_early = sum(((p.numel() + 3) // 4 * 4) for p in self.params if id(p) in early_ids)
+        self.flat = torch.zeros(acc, dtype=torch.float32, device=self.params[0].device)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+        self._early_work = None
+        self.attach()
+
+    def attach(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+            p._srvp_sink = v
+
+    def zero(self):
+        self.flat.zero_()
+        self._early_work = None
+        self.attach()
+
+    def _reduce(self, t, async_op=False):
+        if dist.get_backend() == 'nccl':
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(t, async_op=async_op)
+        if async_op:
+            w.wait()
+        t.div_(world())
+        return None
+
+    def segment_ready(self):
+        """The `early` parameters' gradients are final: start their all-reduce now (no-op for a single process)."""
+        if world() > 1 and self.n_early > 0 and self._early_work is None:
+            self._early_work = self._reduce(self.flat[:self.n_early], async_op=True) or True
+
+    def allreduce_mean(self):
+        if world() == 1:
+            return
+        if self._early_work is not None:
+            if self.n_early < self.flat.numel():
+                self._reduce(self.flat[self.n_early:])
+            if self._early_work is not True:
+                self._early_work.wait()
+            self._early_work = None
+        else:
+            self._reduce(self.flat)
+
+
+ACTIVE_BUCKET = None     # set by the training loop (bench.py / train.py): DecoderFn.backward calls segment_ready() on it
+
+
 def allreduce_bn_partial(partial, count):
     """Sums a (rows, C, 2) partial-statistics tensor over its rows and over all ranks; returns ((1, C, 2) totals, global count).
 

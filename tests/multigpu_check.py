@@ -1,10 +1,13 @@
-"""Multi-GPU check (run under torchrun with 2+ GPUs): SyncBatchNorm semantics + DDP gradient averaging of the B200 path.
+"""Multi-GPU parity worker (run under torchrun with 2+ GPUs; tests/test_gpu_multigpu.py launches it and checks its verdict):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py
 
-Each rank encodes its shard of the videos with SyncBatchNorm-converted containers; the gathered encodings must equal the
-single-GPU encoding of the full batch (batch statistics are global), and DDP-averaged gradients must equal the single-GPU
-gradients of the same global loss.
+The FULL model (encoder, inference nets, latent loop, decoder, ELBO) runs one training step on a batch sharded over the ranks with the
+reference's multi-GPU semantics -- SyncBatchNorm statistics over the global batch (train.py:283), gradients averaged over the ranks
+(DistributedDataParallel, train.py:314; here parallel.GradBucket's single flat all-reduce) -- and is compared with
+  (a) the CPU fp32 ORACLE on the GLOBAL batch with the same per-video random draws: ELBO terms and running statistics;
+  (b) the oracle run at the storage precision of the CUDA path (EMULATE_BF16) on the GPU: every parameter gradient;
+  (c) this repository's single-GPU run on the global batch: every parameter gradient (tight: same arithmetic, different sharding).
 """
 import os
 import sys
@@ -14,7 +17,20 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from common import build_model, make_input, rel_l2  # noqa: E402
-from srvp_b200 import parallel  # noqa: E402
+from srvp_b200 import elbo, parallel  # noqa: E402
+from oracle import srvp_oracle as O  # noqa: E402  (the checker; never the thing measured)
+
+
+def slice_randoms(rnd, lo, hi):
+    out = {}
+    for k, v in rnd.items():
+        if k == 'eps_z':
+            out[k] = [e[lo:hi].contiguous() for e in v]
+        elif k == 't_w':
+            out[k] = v[:, lo:hi].contiguous()
+        else:
+            out[k] = v[lo:hi].contiguous()
+    return out
 
 
 def main():
@@ -24,41 +40,78 @@ def main():
     dist.init_process_group('nccl', device_id=dev)
     cfg = dict(nx=64, nc=3, nf=64, nhx=128, ny=50, nz=50, skipco=True, nt_inf=2, nh_inf=256, nlayers_inf=3, nh_res=512, nlayers_res=4,
                archi='vgg')
-    T, B = 4, 8
-    x = make_input(T, B, 3, 5).to(dev)
+    loss_cfg = dict(obs_scale=0.71, beta_y=1.0, beta_z=1.0, l2_res=1.0)
+    T, B, dt = 6, 8 * world, 0.5
+    x = make_input(T, B, 3, 5)
+    torch.manual_seed(7)
+    rnd = O.draw_randoms(cfg, T, T, B, training=True)          # identical on every rank (same seed)
     lo, hi = parallel.shard_bounds(B, rank, world)
 
-    # reference: single-GPU global batch (plain BatchNorm2d containers)
-    m1 = build_model(cfg, 1.41, 1).to(dev).train()
-    hx1, _ = m1._encode_fused(x)
-    wsum = torch.linspace(0.5, 1.5, 128, device=dev)
-    (hx1 * wsum).sum().backward()
-    g1 = {k: p.grad.clone() for k, p in m1.encoder.named_parameters()}
+    # ours, sharded: SyncBatchNorm containers + one flat gradient all-reduce
+    m = build_model(cfg, 1.41, 1)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m).to(dev).train()
+    bucket = parallel.GradBucket(list(m.parameters()), early=list(m.decoder.parameters()))
+    parallel.ACTIVE_BUCKET = bucket
+    bucket.zero()
+    m.injected_randoms = slice_randoms(rnd, lo, hi)
+    xs = x[:, lo:hi].contiguous().to(dev)
+    out = m(xs, T, dt=dt)
+    loss, nll, kl_y, kl_z = elbo.elbo(out, xs, **loss_cfg)
+    loss.backward()
+    bucket.allreduce_mean()
+    terms = torch.stack([loss.detach(), nll.detach(), kl_y.detach(), kl_z.detach()]).double()
+    dist.all_reduce(terms)
+    terms[0] /= world                                            # loss is batch-averaged per rank; the others are sums
+    g_sharded = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    parallel.ACTIVE_BUCKET = None
 
-    # ours: sharded batch, SyncBatchNorm containers, DDP wrapper (reference train.py:283, :314)
-    m2 = build_model(cfg, 1.41, 1)
-    m2 = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m2).to(dev).train()
-    hx2, _ = m2._encode_fused(x[:, lo:hi].contiguous())
-    (hx2 * wsum).sum().backward()
-    enc_params = [p for p in m2.encoder.parameters()]
-    # DDP would average; the reference loss is a SUM over videos divided by the per-rank batch, here we compare sums: all-reduce SUM
-    flat = torch._utils._flatten_dense_tensors([p.grad for p in enc_params])
-    dist.all_reduce(flat)
-    for p, g in zip(enc_params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in enc_params])):
-        p.grad.copy_(g)
-    gathered = [torch.empty_like(hx2) for _ in range(world)] if B % world == 0 else None
-    dist.all_gather(gathered, hx2.contiguous())
-    hx_all = torch.cat(gathered, 1)
-    e_hx = rel_l2(hx_all, hx1)
-    errs = sorted((rel_l2(p.grad, g1[k]), k) for k, p in m2.encoder.named_parameters())
-    rs = max(rel_l2(b2.running_var, b1.running_var) for b1, b2 in zip([m for m in m1.encoder.modules() if isinstance(m, torch.nn.BatchNorm2d)],
-                                                                   [m for m in m2.encoder.modules() if isinstance(m, torch.nn.SyncBatchNorm)]))
+    ok = True
     if rank == 0:
-        print(f'world={world} hx rel_l2 {e_hx:.3e}; encoder grad rel_l2 median {errs[len(errs) // 2][0]:.3e} max {errs[-1][0]:.3e} ({errs[-1][1]}); '
-              f'max running_var rel over all encoder BN layers {rs:.2e}')
-        ok = e_hx < 3e-2 and rs < 2e-2
-        print('MULTIGPU CHECK', 'PASS' if ok else 'FAIL')
+        # (a) CPU fp32 oracle on the global batch
+        with torch.no_grad():
+            o = O.forward(sd0, cfg, x, T, dt, rnd, training=True)
+            ref = [float(v) for v in O.elbo(o, x, loss_cfg)]
+        rel = [abs(float(terms[i]) - ref[i]) / abs(ref[i]) for i in range(4)]
+        print(f'world={world} ELBO {float(terms[0]):.4f} vs oracle {ref[0]:.4f}: rel loss {rel[0]:.2e} nll {rel[1]:.2e} kl_y {rel[2]:.2e} kl_z {rel[3]:.2e}')
+        ok &= rel[0] < 1e-4 and rel[1] < 1e-4 and rel[2] < 1e-2 and rel[3] < 1e-2
+        # running statistics = those of the global batch (oracle: F.batch_norm on the global batch updates clones; recompute here)
+        st = {}
+        with torch.no_grad():
+            O.forward(sd0, cfg, x, T, dt, rnd, training=True, stats_out=st)
+        worst = 0.0
+        sd = m.state_dict()
+        for prefix, (mean, var) in st.items():
+            worst = max(worst, float((sd[prefix + '.running_mean'].cpu() - 0.1 * mean).abs().max()),
+                        float((sd[prefix + '.running_var'].cpu() - (0.9 + 0.1 * var)).abs().max() / (1 + float(var.abs().max()))))
+        print(f'  running statistics vs global-batch oracle: worst abs deviation {worst:.2e}')
+        ok &= worst < 2e-2
+        # (b) every parameter gradient vs the bf16-emulating oracle on the GPU (fp32 arithmetic, TF32 off)
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        O.EMULATE_BF16, O.USE_ATEN_LSTM = True, False
+        try:
+            sdo = {k: v.to(dev).clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in sd0.items()}
+            rg = {k: ([e.to(dev) for e in v] if isinstance(v, list) else v.to(dev)) for k, v in rnd.items()}
+            O.elbo(O.forward(sdo, cfg, x.to(dev), T, dt, rg, training=True), x.to(dev), loss_cfg)[0].backward()
+        finally:
+            O.EMULATE_BF16, O.USE_ATEN_LSTM = False, True
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        e_or = sorted((rel_l2(g_sharded[k], sdo[k].grad), k) for k in g_sharded)
+        print(f'  gradients vs bf16-emulating oracle (global batch): median rel-L2 {e_or[len(e_or) // 2][0]:.3e}, worst {e_or[-1][0]:.3e} ({e_or[-1][1]})')
+        ok &= e_or[len(e_or) // 2][0] < 5e-2 and e_or[-1][0] < 0.2
+        # (c) single-GPU run of this repository on the global batch
+        m1 = build_model(cfg, 1.41, 1).to(dev).train()
+        m1.injected_randoms = rnd
+        out1 = m1(x.to(dev), T, dt=dt)
+        elbo.elbo(out1, x.to(dev), **loss_cfg)[0].backward()
+        e_1 = sorted((rel_l2(g_sharded[k], p.grad), k) for k, p in m1.named_parameters())
+        print(f'  gradients vs single-GPU run (global batch): median rel-L2 {e_1[len(e_1) // 2][0]:.3e}, worst {e_1[-1][0]:.3e} ({e_1[-1][1]})')
+        ok &= e_1[len(e_1) // 2][0] < 2e-2 and e_1[-1][0] < 0.15
+        print('MULTIGPU CHECK', 'PASS' if ok else 'FAIL', flush=True)
+    dist.barrier()
     dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == '__main__':
