@@ -393,6 +393,18 @@ int srvp_latent_bwd(const srvp_latent_bwd_args* args, void* stream);
 /* out[c] += sum over rows of in[r*ld + c] (bias gradients); dtype SRVP_F32 or SRVP_BF16. */
 int srvp_colsum(const void* in, int32_t dtype, int64_t rows, int32_t cols, int64_t ld, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics of the rollout path, one launch for both:
+ *   out_mse[p]  = mean over the plane of (clamp(pred) - target)^2          (test.py:249: F.mse_loss(...).mean([3, 4]); PSNR = 10 log10(1/mse))
+ *   out_ssim[p] = mean of the SSIM map of the plane                         (test.py:251 _ssim_wrapper -> metrics/ssim.py:81-111: 11x11 Gaussian
+ *                 window sigma 1.5 without padding, k1 0.01, k2 0.03, max_val 1)
+ * pred: (planes, H, W) fp32, target: (target_planes, H, W) fp32 with planes % target_planes == 0 -- plane p is compared with target
+ * plane p % target_planes (n_samples predictions per ground-truth video, sample-major). clamp01: clamp the prediction to [0, 1]
+ * first (test.py:246 `.clamp(0, 1)`).
+ * ---------------------------------------------------------------------------------------------- */
+int srvp_psnr_ssim(const float* pred, const float* target, int64_t planes, int64_t target_planes, int32_t H, int32_t W, int32_t clamp01,
+                   float* out_mse, float* out_ssim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

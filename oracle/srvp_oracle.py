@@ -153,7 +153,8 @@ def lstm(sd, hx):
     nh = wh.shape[1]
     if USE_ATEN_LSTM:  # same fused CPU kernel as nn.LSTM: makes the pinning against the reference bit-exact
         z0 = hx.new_zeros(1, hx.shape[1], nh)
-        return torch._VF.lstm(hx, (z0, z0), [wi, wh, bi, bh], True, 1, 0.0, False, False, False)[0]
+        # train flag: only dropout (0.0 here) depends on it on CPU; cuDNN needs it set to run the backward pass (bench.py's eager-GPU leg)
+        return torch._VF.lstm(hx, (z0, z0), [wi, wh, bi, bh], True, 1, 0.0, hx.is_cuda and torch.is_grad_enabled(), False, False)[0]
     h = hx.new_zeros(hx.shape[1], nh)
     c = hx.new_zeros(hx.shape[1], nh)
     out = []
