@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
 }  // namespace
 
 int num_sms_cached();
+int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream);   // wgrad3x3_tma.cu
 
 }  // namespace srvp
 
@@ -277,6 +278,12 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   SRVP_REQUIRE(a != nullptr && a->dw != nullptr && a->dz != nullptr && a->act != nullptr, "wgrad3x3: null argument");
   SRVP_REQUIRE(a->act_channels % 8 == 0 && a->act_cpitch % 8 == 0 && a->act_coff % 8 == 0, "wgrad3x3: bad activation layout");
   SRVP_REQUIRE(a->dz_channels % 8 == 0 && a->dz_cpitch % 8 == 0 && a->dz_coff % 8 == 0, "wgrad3x3: bad dz layout");
+  // 3x3 layers whose operands are multiples of 64 channels take the TMA-fed kernel (wgrad3x3_tma.cu); thin operands (the first
+  // encoder / last decoder layer) and the 4x4 stride-2 family stay on the cp.async kernel below
+  {
+    const int r = wgrad3x3_tma_try(a, stream);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   WgradDev d{};
   d.act = PlainDev{reinterpret_cast<const __nv_bfloat16*>(a->act), a->act_channels, a->act_cpitch, a->act_coff};
   d.dz = PlainDev{reinterpret_cast<const __nv_bfloat16*>(a->dz), a->dz_channels, a->dz_cpitch, a->dz_coff};

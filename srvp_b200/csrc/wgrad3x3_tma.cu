@@ -1,0 +1,296 @@
+// Weight gradient of the 3x3 / stride 1 / pad 1 convolutions, TMA-fed variant (sm_100a): tensor-map TMA + tcgen05 + TMEM.
+//
+// Same contraction as wgrad3x3.cu (reference: weight half of convolution_backward for module/conv.py:198-220, :333-354, run by
+// loss.backward(), train.py:119):
+//     dW[co, ci, ky, kx] = sum over pixels p of  dz[p, co] * a[p + (ky-1, kx-1), ci]
+// What changed against wgrad3x3.cu (whose 256 cp.async threads fetched 16-byte pieces = half-used 32-byte L2 sectors, staged the halo
+// operand twice per 128 pixels and split the nine taps over two CTAs that each loaded everything; profiles/r01m_wgrad_ablate.log):
+//   * operands arrive by TENSOR-MAP TMA (cp.async.bulk.tensor.4d, one issuing thread): the NHWC tensors are described as
+//     (C, W, H, F); a box is (64 channels, W+2, rows, 1) -- whole 128-byte channel runs, full L2 sectors. The zero padding of the
+//     convolution IS the TMA out-of-bound fill: the activation box starts at x = -1, y = y0-1, the dz box covers x in [0, W+2).
+//   * shared-memory tiles are rows of 128 B (one pixel x 64 channels) in the SWIZZLE_128B canonical MN-major UMMA layout, exactly
+//     what TMA writes; a 3x3 tap is a start-address shift of (ky*(W+2) + kx) rows (validated by probe/umma_sw128_probe.cu).
+//   * TAP FUSION: the descriptor's leading-dimension offset (stride between 64-channel blocks of the M operand) is set to the byte
+//     distance between two taps, so ONE M = 128 MMA multiplies two taps x 64 activation channels: the nine taps take 5 MMAs
+//     (pairs (0,1) (3,4) (6,7) one pixel apart, (2,5) one image row apart, 8 alone) instead of 9, their accumulators (5 x 64 fp32
+//     columns) fit in TMEM at once, so one CTA owns ALL taps of its (64 x 64)-channel block and every tile is loaded once.
+//
+// One CTA: (64 activation channels) x (64 dz channels) x 9 taps x (a contiguous range of pixel stripes); split-K partial results
+// are added to the fp32 gradient with red.global.add.f32. Warps 0-3: epilogue (TMEM lane quarter = warp id), warp 4: TMA producer
+// (one thread), warp 5: MMA issuer (one thread).
+#include <cstdlib>
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/srvp_b200.h"
+
+namespace srvp {
+
+namespace {
+
+constexpr int kTThreads = 192;
+constexpr int kMaxOps = 5;
+constexpr int kMaxStg = 8;
+
+struct TapOp {
+  uint32_t m_off;   // start-address shift of the activation operand, 16-byte units (first tap of the pair)
+  uint32_t m_lbo;   // distance between the two fused taps, 16-byte units
+  int32_t col;      // first TMEM column of this op's accumulators
+  int32_t tap[2];   // 3x3 tap (ky*3+kx) of lanes 0-63 / 64-127; -1 = unused half
+};
+
+struct WgTmaDev {
+  int F, H, W, Wp;
+  int RB, HB, NSUB;          // image rows per stripe, stripes per frame, stripes per pipeline stage
+  int total_subs;            // F * HB
+  int stages_total, splits;
+  int num_mblk, num_nblk;    // 64-channel blocks of the activation / dz operand
+  int ksteps;                // MMA K steps (16 pixels) per stripe
+  uint32_t a_block_bytes, d_block_bytes, sub_bytes, stage_bytes, tx_bytes;
+  int nstg;
+  int nops;
+  TapOp ops[kMaxOps];
+  float* dw;
+  long long stride_cin, stride_cout;
+  int flip, cin_real, cout_real;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+// SWIZZLE_128B canonical layout, MN-major: rows of 128 B (64 channels of one K index); SBO = 8 rows = 1024 B; LBO = stride between
+// 64-channel blocks of the operand (here: between the two fused taps). Fields in 16-byte units.
+__device__ __forceinline__ uint64_t sw128_desc_hi(uint32_t lbo16) {
+  return ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_dz,
+                                                                     const WgTmaDev p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.nstg * p.stage_bytes);
+  uint64_t* full = bars;                // [kMaxStg]
+  uint64_t* empty = bars + kMaxStg;     // [kMaxStg]
+  uint64_t* acc_full = bars + 2 * kMaxStg;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStg + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < p.nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // rows of the tiles that no TMA box ever writes (K padding of the dz tile, tap over-run of the activation tile) must read as
+  // zeros / finite values: clear everything once
+  for (size_t i = tid; i < (size_t)p.nstg * p.stage_bytes / 16; i += kTThreads) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int pairs = p.num_mblk * p.num_nblk;
+  const int pair = blockIdx.x % pairs, split = blockIdx.x / pairs;
+  const int mblk = pair / p.num_nblk, nblk = pair % p.num_nblk;
+  const int steps_per = (p.stages_total + p.splits - 1) / p.splits;
+  const int s0 = split * steps_per;
+  const int s1 = min(p.stages_total, s0 + steps_per);
+  const int nst = max(0, s1 - s0);
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0 && nst > 0) {
+      for (int i = 0; i < nst; ++i) {
+        const int st = i % p.nstg;
+        mbar_wait(&empty[st], ((i / p.nstg) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[st], p.tx_bytes);
+        uint8_t* sb = tiles + (size_t)st * p.stage_bytes;
+        for (int j = 0; j < p.NSUB; ++j) {
+          const int t = (s0 + i) * p.NSUB + j;
+          int f = t / p.HB;
+          int y0 = (t - f * p.HB) * p.RB;
+          if (t >= p.total_subs) { f = p.F; y0 = 0; }   // past the last stripe: a box entirely out of bounds = zeros
+          tma_load_4d(sb + (size_t)j * p.sub_bytes, &map_act, &full[st], mblk * 64, -1, y0 - 1, f);
+          tma_load_4d(sb + (size_t)j * p.sub_bytes + p.a_block_bytes, &map_dz, &full[st], nblk * 64, 0, y0, f);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && nst > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      uint64_t a_hi[kMaxOps];
+#pragma unroll
+      for (int o = 0; o < kMaxOps; ++o) a_hi[o] = sw128_desc_hi(o < p.nops ? p.ops[o].m_lbo : 8u);
+      const uint64_t b_hi = sw128_desc_hi(8u);
+      const uint32_t tile0 = smem_u32(tiles) >> 4;
+      for (int i = 0; i < nst; ++i) {
+        const int st = i % p.nstg;
+        mbar_wait(&full[st], (i / p.nstg) & 1);
+        tc_fence_after();
+        for (int j = 0; j < p.NSUB; ++j) {
+          const uint32_t a0 = tile0 + (uint32_t)((st * p.stage_bytes + j * p.sub_bytes) >> 4);
+          const uint32_t b0 = a0 + (p.a_block_bytes >> 4);
+#pragma unroll 1
+          for (int k = 0; k < p.ksteps; ++k) {
+            const uint64_t bd = b_hi | (uint64_t)((b0 + (uint32_t)k * 128u) & 0x3FFFu);
+            const uint32_t acc_on = (i | j | k) != 0;
+#pragma unroll
+            for (int o = 0; o < kMaxOps; ++o) {
+              if (o < p.nops) {
+                const uint64_t ad = a_hi[o] | (uint64_t)((a0 + p.ops[o].m_off + (uint32_t)k * 128u) & 0x3FFFu);
+                umma_bf16(tmem_base + (uint32_t)p.ops[o].col, ad, bd, idesc, acc_on);
+              }
+            }
+          }
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> red.add into dW
+    if (nst > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const int L = warp * 32 + lane;
+      const int tb = L >> 6;
+      const int ci = mblk * 64 + (L & 63);
+      const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int o = 0; o < p.nops; ++o) {
+        const int tap = p.ops[o].tap[tb];
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float vals[32];
+          tmem_ld32(acc + (uint32_t)p.ops[o].col + c0, vals);
+          if (tap >= 0 && ci < p.cin_real) {
+            const int te = p.flip ? 8 - tap : tap;
+            float* dst = p.dw + (long long)ci * p.stride_cin + te;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              const int co = nblk * 64 + c0 + n;
+              if (co < p.cout_real) atomicAdd(dst + (long long)co * p.stride_cout, vals[n]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// (C, W, H, F) view of an NHWC bf16 tensor, box (64, W+2, rows, 1), 128-byte swizzle, zero fill outside the tensor
+int make_map(CUtensorMap* map, const void* base, int channels, int cpitch, int W, int H, int F, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  SRVP_REQUIRE(enc != nullptr, "wgrad3x3_tma: cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
+  cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(W + 2), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRVP_REQUIRE(r == CUDA_SUCCESS, "wgrad3x3_tma: cuTensorMapEncodeTiled failed (%d) for C=%d pitch=%d W=%d H=%d F=%d rows=%d", (int)r, channels, cpitch,
+               W, H, F, box_rows);
+  return 0;
+}
+
+}  // namespace
+
+int num_sms_cached();
+
+// Returns 1 when this launch was taken (0: not eligible -> the caller falls back to the cp.async kernel, < 0: error).
+int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("SRVP_WGRAD_TMA"); enabled = e ? atoi(e) : 1; }
+  if (!enabled || a->map4 != 0) return 0;
+  if (a->act_channels % 64 != 0 || a->dz_channels % 64 != 0 || a->act_channels < 64 || a->dz_channels < 64) return 0;
+  if (a->W + 2 > 160 || a->W < 1 || a->H < 1) return 0;
+  if ((reinterpret_cast<uintptr_t>(a->act) + (size_t)a->act_coff * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->dz) + (size_t)a->dz_coff * 2) % 16 != 0) return 0;
+  WgTmaDev d{};
+  d.F = a->frames; d.H = a->H; d.W = a->W; d.Wp = a->W + 2;
+  // stripe height: the largest divisor of H with at most 160 (W+2)-pixel rows in a stripe
+  int RB = 1;
+  for (int r = 1; r <= a->H; ++r)
+    if (a->H % r == 0 && r * d.Wp <= 160) RB = r;
+  d.RB = RB;
+  d.HB = a->H / RB;
+  const int Kd = RB * d.Wp, Kp = (Kd + 15) / 16 * 16, Ka = (RB + 2) * d.Wp;
+  d.ksteps = Kp / 16;
+  d.NSUB = 160 / Kp < 1 ? 1 : 160 / Kp;
+  d.total_subs = d.F * d.HB;
+  d.stages_total = (d.total_subs + d.NSUB - 1) / d.NSUB;
+  int a_rows = Kp + 2 * d.Wp + 3;           // last K row + largest tap shift (+1: the unused half of the single-tap MMA reads one row further)
+  if (a_rows < Ka) a_rows = Ka;
+  a_rows = (a_rows + 7) / 8 * 8;
+  d.a_block_bytes = (uint32_t)a_rows * 128;
+  d.d_block_bytes = (uint32_t)Kp * 128;
+  d.sub_bytes = d.a_block_bytes + d.d_block_bytes;
+  d.stage_bytes = d.sub_bytes * d.NSUB;
+  d.tx_bytes = (uint32_t)d.NSUB * (uint32_t)(Ka + Kd) * 128;
+  int nstg = (int)((227 * 1024 - 2048) / d.stage_bytes);
+  if (nstg > kMaxStg) nstg = kMaxStg;
+  if (nstg < 2) return 0;
+  d.nstg = nstg;
+  d.num_mblk = a->act_channels / 64;
+  d.num_nblk = a->dz_channels / 64;
+  const int sms = num_sms_cached();
+  const int pairs = d.num_mblk * d.num_nblk;
+  int splits = sms / pairs;
+  if (splits < 1) splits = 1;
+  if (splits > d.stages_total) splits = d.stages_total;
+  d.splits = splits;
+  // tap pairs: (0,1) (3,4) (6,7) one pixel apart, (2,5) one image row apart, 8 alone
+  const int pa[5] = {0, 3, 6, 2, 8}, pb[5] = {1, 4, 7, 5, -1};
+  d.nops = 5;
+  for (int o = 0; o < 5; ++o) {
+    const int ky = pa[o] / 3, kx = pa[o] % 3;
+    d.ops[o].m_off = (uint32_t)(ky * d.Wp + kx) * 8u;
+    d.ops[o].m_lbo = (pb[o] >= 0 && pb[o] - pa[o] == 3) ? (uint32_t)d.Wp * 8u : 8u;
+    d.ops[o].col = o * 64;
+    d.ops[o].tap[0] = pa[o];
+    d.ops[o].tap[1] = pb[o];
+  }
+  d.dw = a->dw;
+  d.stride_cin = a->stride_cin; d.stride_cout = a->stride_cout;
+  d.flip = a->flip & 1;
+  d.cin_real = a->cin; d.cout_real = a->cout;
+  CUtensorMap map_act, map_dz;
+  if (make_map(&map_act, reinterpret_cast<const uint16_t*>(a->act) + a->act_coff, a->act_channels, a->act_cpitch, a->W, a->H, a->frames, RB + 2) != 0) return -1;
+  if (make_map(&map_dz, reinterpret_cast<const uint16_t*>(a->dz) + a->dz_coff, a->dz_channels, a->dz_cpitch, a->W, a->H, a->frames, RB) != 0) return -1;
+  const size_t smem = (size_t)nstg * d.stage_bytes + 1024 /* alignment slack */ + (2 * kMaxStg + 2) * 8;
+  SRVP_REQUIRE(smem <= 227 * 1024, "wgrad3x3_tma: shared memory %zu B exceeds 227 KB", smem);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad3x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    SRVP_REQUIRE(e == cudaSuccess, "wgrad3x3_tma: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;   // one CTA per SM (all 512 TMEM columns are allocated)
+  wgrad3x3_tma_kernel<<<pairs * splits, kTThreads, smem_launch, stream>>>(map_act, map_dz, d);
+  const int rc = check_launch("wgrad3x3_tma");
+  return rc != 0 ? rc : 1;
+}
+
+}  // namespace srvp
