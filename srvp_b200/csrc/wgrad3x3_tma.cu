@@ -27,7 +27,7 @@ namespace srvp {
 
 namespace {
 
-constexpr int kTThreads = 192;
+constexpr int kTThreads = 224;   // warps 0-3 epilogue, 4 TMA producer, 5-6 MMA issuers
 constexpr int kMaxOps = 5;
 constexpr int kMaxStg = 8;
 
@@ -52,6 +52,8 @@ struct WgTmaDev {
   float* dw;
   long long stride_cin, stride_cout;
   int flip, cin_real, cout_real;
+  int issuers;   // MMA-issuing threads (1 or 2): the five ops are split 3 + 2
+  int dbg;       // development (env SRVP_WGRAD_DBG): 1 = no TMA loads, 2 = no MMAs
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -78,8 +80,8 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < p.nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < p.nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.issuers); }
+    mbar_init(acc_full, p.issuers);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
       for (int i = 0; i < nst; ++i) {
         const int st = i % p.nstg;
         mbar_wait(&empty[st], ((i / p.nstg) & 1) ^ 1);
+        if (p.dbg & 1) { mbar_arrive(&full[st]); continue; }
         mbar_arrive_expect_tx(&full[st], p.tx_bytes);
         uint8_t* sb = tiles + (size_t)st * p.stage_bytes;
         for (int j = 0; j < p.NSUB; ++j) {
@@ -118,9 +121,10 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
         }
       }
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && nst > 0) {
+  } else if (warp == 5 || warp == 6) {
+    // ------------------------------------------------------------------ MMA issuers (warp 6 only with two issuers: ops [o_lo, o_hi) each)
+    const int o_lo = (warp == 5) ? 0 : 3, o_hi = (p.issuers == 1) ? p.nops : (warp == 5 ? 3 : p.nops);
+    if (lane == 0 && nst > 0 && (warp == 5 || p.issuers == 2)) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
       uint64_t a_hi[kMaxOps];
 #pragma unroll
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
             const uint32_t acc_on = (i | j | k) != 0;
 #pragma unroll
             for (int o = 0; o < kMaxOps; ++o) {
-              if (o < p.nops) {
+              if (o >= o_lo && o < o_hi && !(p.dbg & 2)) {
                 const uint64_t ad = a_hi[o] | (uint64_t)((a0 + p.ops[o].m_off + (uint32_t)k * 128u) & 0x3FFFu);
                 umma_bf16(tmem_base + (uint32_t)p.ops[o].col, ad, bd, idesc, acc_on);
               }
@@ -271,6 +275,14 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
     d.ops[o].col = o * 64;
     d.ops[o].tap[0] = pa[o];
     d.ops[o].tap[1] = pb[o];
+  }
+  {
+    static int dbg = -1, iss = -1;
+    if (dbg < 0) { const char* e = getenv("SRVP_WGRAD_DBG"); dbg = e ? atoi(e) : 0; }
+    if (iss < 0) { const char* e = getenv("SRVP_WGRAD_ISSUERS"); iss = e ? atoi(e) : 1; if (iss != 2) iss = 1; }
+    d.dbg = dbg;
+    d.issuers = iss;
+    if (dbg & 4) for (int o = 0; o < 5; ++o) d.ops[o].m_lbo = 64 * 8;   // timing only: block-aligned second half (wrong numbers)
   }
   d.dw = a->dw;
   d.stride_cin = a->stride_cin; d.stride_cout = a->stride_cout;

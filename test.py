@@ -1,105 +1,129 @@
-"""Evaluation entry point for the hot path (reference: test.py:145-319): conditioning-frame encoding, `n_samples` stochastic
-rollouts per video (posterior on the conditioning frames, prior afterwards), best/worst-by-PSNR bookkeeping, results saved
-as .npz. SSIM / LPIPS / FVD of the reference are third-party evaluation code and out of scope.
+"""Evaluation entry point for the hot path (reference: test.py:145-319): conditioning-frame encoding, `n_samples` stochastic rollouts per
+video (posterior on the conditioning frames, prior afterwards), PSNR and SSIM of every sample (one fused kernel, srvp_b200/metrics.py),
+best / worst sample bookkeeping per metric, results saved as .npz exactly as the reference names them (results.npz with `psnr`, `ssim`;
+`psnr_best.npz`, `ssim_worst.npz`, `random_1.npz` ...). LPIPS and FVD run third-party networks (VGG / I3D weights that cannot be fetched
+here) and are out of scope: --lpips_dir and --fvd are accepted and ignored with a note.
 
-  python test.py --xp_dir RUN_DIR --nt_gen 30 [--data_dir DIR | synthetic frames] [--n_samples 100] [--batch_size 16]
+  python test.py --xp_dir RUN_DIR --nt_gen 53 [--data_dir DIR | synthetic frames] [--n_samples 100] [--batch_size 16]
+
+Every option of the reference's test.py:331-354 is accepted. `--sample_batch 0` runs the reference's own loop (one sample at a time through
+the public forward / generate / decode API) instead of the batched rollout (srvp_b200/rollout.py).
 """
 import argparse
 import json
 import os
+from collections import defaultdict
 
 import numpy as np
 import torch
 
+from srvp_b200 import metrics, rollout
 from srvp_b200.module import srvp
 
 
-def psnr(x, y):
-    """Peak signal-to-noise ratio per (frame, video) for tensors in [0, 1] of shape (T, B, C, H, W)."""
-    mse = ((x - y) ** 2).flatten(2).mean(2)
-    return 10 * torch.log10(1 / mse.clamp_min(1e-12))
-
-
-def main(opt):
-    device = torch.device('cuda', opt.device)
-    torch.cuda.set_device(device)
-    torch.manual_seed(opt.seed)
-    np.random.seed(opt.seed)
-    cfg = json.load(open(os.path.join(opt.xp_dir, 'config.json')))
+def load_model(xp_dir, model_name, device):
+    cfg = json.load(open(os.path.join(xp_dir, 'config.json')))
     model = srvp.StochasticLatentResidualVideoPredictor(cfg['nx'], cfg['nc'], cfg['nf'], cfg['nhx'], cfg['ny'], cfg['nz'], cfg['skipco'],
                                                         cfg['nt_inf'], cfg['nh_inf'], cfg['nlayers_inf'], cfg['nh_res'], cfg['nlayers_res'],
                                                         cfg['archi'])
-    model.load_state_dict(torch.load(os.path.join(opt.xp_dir, opt.model_name), map_location='cpu'))
-    model.to(device).eval()
+    model.load_state_dict(torch.load(os.path.join(xp_dir, model_name), map_location='cpu'))
+    return model.to(device).eval(), cfg
+
+
+def reference_loop(model, x, nt_cond, n_samples, dt_cond, dt_gen):
+    """The reference's per-sample loop (test.py:235-254) through the public API; returns (psnr, ssim) (n_samples, B) and the samples."""
+    x_cond, x_target = x[:nt_cond], x[nt_cond:]
+    skip = model.encode(x_cond)[1] if model.skipco else None           # eval mode: skips from the last conditioning frame
+    ps, ss, preds = [], [], []
+    for _ in range(n_samples):
+        _, y, _, w, _, _, _, _ = model(x_cond, nt_cond, dt=dt_cond)    # posterior pass on the conditioning frames
+        y_os = model.generate(y[-1], [], x.shape[0] - nt_cond + 1, dt=dt_gen)[0]   # hx=[]: pure prior rollout
+        x_pred = model.decode(w, y_os[1:].contiguous(), skip).clamp(0, 1)
+        p, s = metrics.psnr_ssim(x_pred, x_target, clamp=False)         # (T', B, C)
+        ps.append(p.mean(2).mean(0))
+        ss.append(s.mean(2).mean(0))
+        preds.append(x_pred)
+    return torch.stack(ps), torch.stack(ss), torch.stack(preds)
+
+
+def to_bytes(x):
+    """(T, B, C, H, W) in [0, 1] -> uint8 (B, T, H, W, C) as the reference stores samples (test.py:217)."""
+    return x.mul(255).byte().permute(1, 0, 3, 4, 2).cpu()
+
+
+def main(opt):
+    if opt.device is None:
+        raise RuntimeError('srvp_b200 has no CPU path: pass --device (a CUDA device index)')
+    device = torch.device('cuda', opt.device)
+    torch.cuda.set_device(device)
+    torch.manual_seed(opt.test_seed)
+    np.random.seed(opt.test_seed)
+    if opt.lpips_dir is not None or opt.fvd:
+        print('srvp_b200: LPIPS / FVD are outside the hot path (third-party networks); --lpips_dir / --fvd are ignored')
+    model, cfg = load_model(opt.xp_dir, opt.model_name, device)
     torch.set_grad_enabled(False)
-    nt_cond = cfg['nt_cond']
-    dt = 1 / cfg['n_euler_steps']
+    nt_cond = opt.nt_cond if opt.nt_cond is not None else cfg['nt_cond']
+    nt_test = opt.nt_gen if opt.nt_gen is not None else (cfg.get('seq_len_test') or cfg['seq_len'])
+    dt_train = 1 / cfg['n_euler_steps']
+    dt_gen = 1 / (opt.n_euler_steps if opt.n_euler_steps is not None else cfg['n_euler_steps'])
     if opt.data_dir is not None:
-        videos = np.load(os.path.join(opt.data_dir, 'videos.npz'))['videos']
-        data = torch.from_numpy(videos).permute(1, 0, 4, 2, 3).float() / 255          # (T, N, C, H, W)
+        videos = np.load(os.path.join(opt.data_dir, 'videos.npz'))['videos']                   # uint8 (N, T, H, W, C)
+        data = torch.from_numpy(videos).permute(1, 0, 4, 2, 3).float() / 255                  # (T, N, C, H, W)
     else:
-        data = torch.rand(opt.nt_gen, opt.n_videos, cfg['nc'], cfg['nx'], cfg['nx'], generator=torch.Generator().manual_seed(opt.seed))
-    nt_test = min(opt.nt_gen, data.shape[0])
-    best, worst, scores = [], [], []
+        data = torch.rand(nt_test, opt.n_videos, cfg['nc'], cfg['nx'], cfg['nx'], generator=torch.Generator().manual_seed(opt.test_seed))
+    assert nt_test <= data.shape[0]
+    results, best_samples, worst_samples = defaultdict(list), defaultdict(list), defaultdict(list)
+    random_samples = [[] for _ in range(min(5, opt.n_samples))]
     for b0 in range(0, data.shape[1], opt.batch_size):
         x = data[:nt_test, b0:b0 + opt.batch_size].to(device)
-        x_cond, x_target = x[:nt_cond], x[nt_cond:]
         bsz = x.shape[1]
-        all_psnr, all_pred = [], []
-        if opt.sample_batch <= 0:
-            # the reference's loop (test.py:235-246), one sample at a time through the public API
-            skip = model.encode(x_cond)[1] if model.skipco else None           # eval mode: skips from the last conditioning frame
-            for _ in range(opt.n_samples):
-                _, y, _, w, _, _, _, _ = model(x_cond, nt_cond, dt=dt)           # posterior pass on the conditioning frames
-                y_os = model.generate(y[-1], [], nt_test - nt_cond + 1, dt=dt)[0]   # hx=[]: pure prior rollout
-                x_pred = model.decode(w, y_os[1:], skip).clamp(0, 1)
-                all_psnr.append(psnr(x_pred, x_target).mean(0))
-                all_pred.append(x_pred.cpu())
+        if opt.sample_batch <= 0 or dt_gen != dt_train:
+            ps, ss, pred = reference_loop(model, x, nt_cond, opt.n_samples, dt_train, dt_gen)
         else:
-            # Same computation with the deterministic work hoisted and the samples batched: in eval mode the encoder,
-            # the skip features and w do not depend on the sample (the reference re-runs the encoder n_samples times, test.py:237-239
-            # and decodes the conditioning frames it never uses); only y_0, the posterior / prior z and the decoded rollout do.
-            hx, handle = model._encode_fused(x_cond)
-            w = model.infer_w(hx)
-            levels = handle.levels if handle is not None else None
-            sel = handle.frame_map if handle is not None else None
-            done = 0
-            while done < opt.n_samples:
-                sc = min(opt.sample_batch, opt.n_samples - done)
-                hx_rep = hx.repeat(1, sc, 1)                                     # (nt_cond, sc * B, nhx), sample-major
-                y_0, _ = model.infer_y(hx_rep[:model.nt_inf])
-                y = model.generate(y_0, hx_rep, nt_cond, dt=dt)[0]               # posterior on the conditioning frames
-                y_os = model.generate(y[-1], [], nt_test - nt_cond + 1, dt=dt)[0]   # prior rollout
-                x_pred = model._decode_fused(w.repeat(sc, 1), y_os[1:], levels, sel.repeat(sc) if sel is not None else None, None)
-                x_pred = x_pred.clamp(0, 1).view(x_pred.shape[0], sc, bsz, *x_pred.shape[2:])
-                for si in range(sc):
-                    all_psnr.append(psnr(x_pred[:, si], x_target).mean(0))
-                    all_pred.append(x_pred[:, si].cpu())
-                done += sc
-        ps = torch.stack(all_psnr)                                              # (n_samples, B)
-        pred = torch.stack(all_pred)                                            # (n_samples, T', B, C, H, W)
-        bi, wi = ps.argmax(0).cpu(), ps.argmin(0).cpu()
-        ar = torch.arange(ps.shape[1])
-        best.append(pred[bi, :, ar].transpose(0, 1))
-        worst.append(pred[wi, :, ar].transpose(0, 1))
-        scores.append(ps.max(0)[0].cpu())
-    scores = torch.cat(scores)
-    ci = 1.96 * scores.std() / max(1, len(scores)) ** 0.5
-    print(f'PSNR (best of {opt.n_samples}): {scores.mean():.4f} +/- {ci:.4f}')
-    np.savez_compressed(os.path.join(opt.xp_dir, 'results.npz'), psnr=scores.numpy(),
-                        best=(torch.cat(best, 1) * 255).byte().numpy(), worst=(torch.cat(worst, 1) * 255).byte().numpy())
+            r = rollout.best_of_n(model, x, nt_cond, opt.n_samples, dt_train, sample_batch=opt.sample_batch, keep_samples=True)
+            ps, ss, pred = r['psnr'], r['ssim'], r['samples']                                   # (S, B), (S, B), (S, T', B, C, H, W)
+        ar = torch.arange(bsz, device=device)
+        for name, vals in (('psnr', ps), ('ssim', ss)):
+            bi, wi = vals.argmax(0), vals.argmin(0)
+            results[name].append(vals.max(0)[0].cpu())
+            best_samples[name].append(to_bytes(pred[bi, :, ar].transpose(0, 1)))
+            worst_samples[name].append(to_bytes(pred[wi, :, ar].transpose(0, 1)))
+        for i in range(len(random_samples)):
+            random_samples[i].append(to_bytes(pred[i]))
+    print('\nResults:')
+    out = {}
+    for name, res in results.items():
+        res = torch.cat(res).numpy()
+        out[name] = res
+        print(name, res.mean(), '+/-', 1.960 * res.std() / np.sqrt(len(res)))
+    np.savez_compressed(os.path.join(opt.xp_dir, 'results.npz'), **out)
+    for i, rs in enumerate(random_samples):
+        np.savez_compressed(os.path.join(opt.xp_dir, f'random_{i + 1}.npz'), samples=torch.cat(rs).numpy())
+    for name in best_samples:
+        np.savez_compressed(os.path.join(opt.xp_dir, f'{name}_best.npz'), samples=torch.cat(best_samples[name]).numpy())
+        np.savez_compressed(os.path.join(opt.xp_dir, f'{name}_worst.npz'), samples=torch.cat(worst_samples[name]).numpy())
+    return out
+
+
+def create_args():
+    p = argparse.ArgumentParser(prog='Stochastic Latent Residual Video Prediction (testing, B200-native hot path)', description=__doc__,
+                                formatter_class=argparse.RawDescriptionHelpFormatter)
+    p.add_argument('--xp_dir', type=str, required=True)
+    p.add_argument('--data_dir', type=str, default=None, help='directory with videos.npz (uint8 (N, T, H, W, C)); synthetic frames if omitted')
+    p.add_argument('--lpips_dir', type=str, default=None, help='accepted for compatibility, ignored')
+    p.add_argument('--n_euler_steps', type=int, default=None)
+    p.add_argument('--nt_cond', type=int, default=None)
+    p.add_argument('--nt_gen', type=int, default=None)
+    p.add_argument('--batch_size', type=int, default=16)
+    p.add_argument('--n_samples', type=int, default=100)
+    p.add_argument('--model_name', type=str, default='model.pt')
+    p.add_argument('--device', type=int, default=0)
+    p.add_argument('--fvd', action='store_true', help='accepted for compatibility, ignored')
+    p.add_argument('--test_seed', '--seed', type=int, default=1)
+    p.add_argument('--n_videos', type=int, default=16, help='synthetic data only')
+    p.add_argument('--sample_batch', type=int, default=25, help='samples decoded per launch; 0 = the reference loop, one sample at a time')
+    return p
 
 
 if __name__ == '__main__':
-    p = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    p.add_argument('--xp_dir', type=str, required=True)
-    p.add_argument('--model_name', type=str, default='model.pt')
-    p.add_argument('--data_dir', type=str, default=None)
-    p.add_argument('--nt_gen', type=int, required=True)
-    p.add_argument('--n_samples', type=int, default=100)
-    p.add_argument('--n_videos', type=int, default=16)
-    p.add_argument('--batch_size', type=int, default=16)
-    p.add_argument('--sample_batch', type=int, default=25, help='samples decoded per launch; 0 = the reference loop, one sample at a time')
-    p.add_argument('--device', type=int, default=0)
-    p.add_argument('--seed', type=int, default=1)
-    main(p.parse_args())
+    main(create_args().parse_args())

@@ -11,6 +11,9 @@ LAYERS = [('64->64@64', 64, 64, 64, F_), ('64->128@32', 64, 128, 32, F_), ('128-
           ('128->256@16', 128, 256, 16, F_), ('256->128@16', 256, 128, 16, F_), ('256->256@16', 256, 256, 16, F_), ('256->512@8', 256, 512, 8, F_),
           ('512->256@8', 512, 256, 8, F_), ('512->512@8', 512, 512, 8, F_), ('skip 512->512@8 (B frames)', 512, 512, 8, F_ // 12),
           ('skip 64->64@64 (B frames)', 64, 64, 64, F_ // 12)]
+sel = os.environ.get('LAYERS')
+if sel:
+    LAYERS = [l for l in LAYERS if l[0] in sel.split(',')]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 tot = 0.0
 for name, cin, cout, H, fr in LAYERS:

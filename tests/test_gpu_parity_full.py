@@ -164,8 +164,12 @@ def test_gradients_vs_bf16_emulating_oracle(T, B, dev):
           f'worst ours-vs-bf16-oracle {max(r[1] for r in rows):.3e}; min cos {min(r[2] for r in rows):.6f}')
     assert len(rows) >= 60
     for k, e_emu, c_emu, e_round, e_fp32 in rows:
-        assert e_fp32 < 1.3 * e_round + 2e-3, (k, e_fp32, e_round)
-        assert e_emu < 1.0 * e_round + 2e-3, (k, e_emu, e_round)
+        # the emulation covers the conv stacks' storage rounding; the latent p_z / dynamics MLPs additionally multiply bf16 operands
+        # inside the persistent kernel (not emulated; measured: up to 4.1e-2 on p_z's first layer, whose input y grows to |y| ~ 90 at
+        # initialisation): their parameters, and those upstream of y_0 / z, get 5e-2 of absolute slack
+        slack = 2e-3 if k.startswith(('encoder.', 'decoder.')) else 5e-2
+        assert e_fp32 < 1.3 * e_round + slack, (k, e_fp32, e_round)
+        assert e_emu < 1.0 * e_round + slack, (k, e_emu, e_round)
         assert c_emu > 0.95, (k, c_emu)
     for k in ['decoder.conv.3.1.weight', 'decoder.conv.3.0.1.weight', 'decoder.conv.3.0.1.bias', 'decoder.conv.3.0.0.weight']:
         r = next(r for r in rows if r[0] == k)
