@@ -27,7 +27,7 @@ namespace srvp {
 
 namespace {
 
-constexpr int kTThreads = 224;   // warps 0-3 epilogue, 4 TMA producer, 5-6 MMA issuers
+constexpr int kTThreads = 192;   // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
 constexpr int kMaxOps = 5;
 constexpr int kMaxStg = 8;
 
@@ -52,14 +52,31 @@ struct WgTmaDev {
   float* dw;
   long long stride_cin, stride_cout;
   int flip, cin_real, cout_real;
-  int issuers;   // MMA-issuing threads (1 or 2): the five ops are split 3 + 2
-  int dbg;       // development (env SRVP_WGRAD_DBG): 1 = no TMA loads, 2 = no MMAs
+  int dbg;       // development (env SRVP_WGRAD_DBG): 1 = no TMA loads, 2 = no MMAs, 8 = no epilogue, 16 = scalar-atomic epilogue
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+
+// One lane of a converged warp (elect.sync).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// tcgen05.mma with the two 64-bit shared-memory descriptors passed as (low, high) register pairs: the issuing thread updates only the
+// low words (start address) with 32-bit adds.
+__device__ __forceinline__ void umma_bf16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // SWIZZLE_128B canonical layout, MN-major: rows of 128 B (64 channels of one K index); SBO = 8 rows = 1024 B; LBO = stride between
@@ -80,8 +97,8 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < p.nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.issuers); }
-    mbar_init(acc_full, p.issuers);
+    for (int i = 0; i < p.nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -93,6 +110,10 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0u) {   // cannot happen for a 512-column allocation; the MMA issuer relies on it
+    if (tid == 0) printf("srvp: wgrad3x3_tma: unexpected TMEM base %u\n", tmem_base);
+    __trap();
+  }
 
   const int pairs = p.num_mblk * p.num_nblk;
   const int pair = blockIdx.x % pairs, split = blockIdx.x / pairs;
@@ -121,63 +142,116 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
         }
       }
     }
-  } else if (warp == 5 || warp == 6) {
-    // ------------------------------------------------------------------ MMA issuers (warp 6 only with two issuers: ops [o_lo, o_hi) each)
-    const int o_lo = (warp == 5) ? 0 : 3, o_hi = (p.issuers == 1) ? p.nops : (warp == 5 ? 3 : p.nops);
-    if (lane == 0 && nst > 0 && (warp == 5 || p.issuers == 2)) {
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    // ONE thread issues every MMA of the CTA, so the loop body must stay at a handful of instructions per MMA: with ~20 instructions
+    // (descriptor assembly, parameter loads, predicates) per MMA the issuing thread, not the tensor core, set the pace -- the kernel took
+    // the same time with the loads, the MMAs and the epilogue all disabled (profiles/r03d_wgrad_ablate.log). Everything that does not
+    // change is therefore hoisted into registers: per op the descriptor's high word, its low word at (stage 0, stripe 0, k 0) and the
+    // TMEM column; per K step only one 32-bit add per descriptor remains.
+    // The WHOLE warp runs the loop converged and only the tcgen05 instructions are predicated on one elected lane: inside a
+    // `lane == 0` branch the compiler cannot use the uniform datapath and wraps every MMA in an elect / R2UR broadcast loop.
+    if (nst > 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
-      uint64_t a_hi[kMaxOps];
-#pragma unroll
-      for (int o = 0; o < kMaxOps; ++o) a_hi[o] = sw128_desc_hi(o < p.nops ? p.ops[o].m_lbo : 8u);
-      const uint64_t b_hi = sw128_desc_hi(8u);
       const uint32_t tile0 = smem_u32(tiles) >> 4;
-      for (int i = 0; i < nst; ++i) {
-        const int st = i % p.nstg;
-        mbar_wait(&full[st], (i / p.nstg) & 1);
-        tc_fence_after();
-        for (int j = 0; j < p.NSUB; ++j) {
-          const uint32_t a0 = tile0 + (uint32_t)((st * p.stage_bytes + j * p.sub_bytes) >> 4);
-          const uint32_t b0 = a0 + (p.a_block_bytes >> 4);
-#pragma unroll 1
-          for (int k = 0; k < p.ksteps; ++k) {
-            const uint64_t bd = b_hi | (uint64_t)((b0 + (uint32_t)k * 128u) & 0x3FFFu);
-            const uint32_t acc_on = (i | j | k) != 0;
+      uint32_t a_lo[kMaxOps], a_hi[kMaxOps], dcol[kMaxOps];
 #pragma unroll
-            for (int o = 0; o < kMaxOps; ++o) {
-              if (o >= o_lo && o < o_hi && !(p.dbg & 2)) {
-                const uint64_t ad = a_hi[o] | (uint64_t)((a0 + p.ops[o].m_off + (uint32_t)k * 128u) & 0x3FFFu);
-                umma_bf16(tmem_base + (uint32_t)p.ops[o].col, ad, bd, idesc, acc_on);
-              }
-            }
-          }
-        }
-        umma_commit(&empty[st]);
+      for (int o = 0; o < kMaxOps; ++o) {
+        a_lo[o] = tile0 + p.ops[o].m_off;                         // < 2^14 for every reachable offset: no carry into the LBO field
+        a_hi[o] = (uint32_t)(sw128_desc_hi(p.ops[o].m_lbo) >> 32);
+        a_lo[o] |= (uint32_t)sw128_desc_hi(p.ops[o].m_lbo);       // LBO lives in bits 16-29 of the low word
+        // The CTA allocates ALL 512 TMEM columns, so the allocation starts at column 0 / lane 0 (checked above): keeping the
+        // accumulator addresses free of the value read back from shared memory keeps them in uniform registers.
+        dcol[o] = (uint32_t)p.ops[o].col;
       }
-      umma_commit(acc_full);
+      const uint32_t b_lo0 = (tile0 + (p.a_block_bytes >> 4)) | (uint32_t)sw128_desc_hi(8u);
+      const uint32_t b_hi = (uint32_t)(sw128_desc_hi(8u) >> 32);
+      const uint32_t stage16 = p.stage_bytes >> 4, sub16 = p.sub_bytes >> 4;
+      const int nsub = p.NSUB, ksteps = p.ksteps, nstg = p.nstg;
+      const bool no_mma = (p.dbg & 2) != 0;
+      uint32_t accf = 0;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nst; ++i) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        uint32_t off = (uint32_t)st * stage16;
+        for (int j = 0; j < nsub; ++j) {
+          uint32_t o16 = off;
+#pragma unroll 1
+          for (int k = 0; k < ksteps; ++k) {
+            if (!no_mma && elect_one()) {
+#pragma unroll
+              for (int o = 0; o < kMaxOps; ++o) umma_bf16_split(dcol[o], a_lo[o] + o16, a_hi[o], b_lo0 + o16, b_hi, idesc, accf);
+            }
+            accf = 1;
+            o16 += 128;     // 16 K rows of 128 B
+          }
+          off += sub16;
+        }
+        if (elect_one()) umma_commit(&empty[st]);
+        if (++st == nstg) { st = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(acc_full);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: TMEM -> red.add into dW
-    if (nst > 0) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> shared memory -> coalesced red.add into dW
+    if (nst > 0 && !(p.dbg & 8)) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const int L = warp * 32 + lane;
       const int tb = L >> 6;
-      const int ci = mblk * 64 + (L & 63);
+      const int cl = L & 63;
+      const int ci = mblk * 64 + cl;
       const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
+      // Fast path (nn.Conv2d weight layout (cout, cin, 3, 3), whole 64-channel blocks): the 64 x 9 gradients of one output channel
+      // of this block are 2304 contiguous bytes of dW. The accumulators are transposed through the (now idle) pipeline buffers into
+      // [co][ci][tap] and added with 16-byte red.global.add.v4.f32 -- 4 full sectors per warp instruction instead of 32 scattered
+      // 4-byte atomics (the scattered version cost more than the whole main loop: profiles/r03c_wgrad_ablate.log).
+      const bool fast = !(p.dbg & 16) && p.flip == 0 && p.stride_cin == 9 && (p.stride_cout % 4) == 0 && (mblk * 64 + 64) <= p.cin_real &&
+                        (nblk * 64 + 64) <= p.cout_real && (reinterpret_cast<uintptr_t>(p.dw) % 16) == 0 && (size_t)p.nstg * p.stage_bytes >= 64 * 576 * 4;
+      if (fast) {
+        float* stg = reinterpret_cast<float*>(tiles);     // [64 co][64 ci][9 taps] fp32 = 147 KB
 #pragma unroll 1
-      for (int o = 0; o < p.nops; ++o) {
-        const int tap = p.ops[o].tap[tb];
+        for (int o = 0; o < p.nops; ++o) {
+          const int tap = p.ops[o].tap[tb];
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          float vals[32];
-          tmem_ld32(acc + (uint32_t)p.ops[o].col + c0, vals);
-          if (tap >= 0 && ci < p.cin_real) {
-            const int te = p.flip ? 8 - tap : tap;
-            float* dst = p.dw + (long long)ci * p.stride_cin + te;
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            float vals[32];
+            tmem_ld32(acc + (uint32_t)p.ops[o].col + c0, vals);
+            if (tap >= 0) {
 #pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              const int co = nblk * 64 + c0 + n;
-              if (co < p.cout_real) atomicAdd(dst + (long long)co * p.stride_cout, vals[n]);
+              for (int n = 0; n < 32; ++n) stg[(c0 + n) * 576 + cl * 9 + tap] = vals[n];   // lanes: stride 9 words = conflict-free
+            }
+          }
+        }
+        named_bar_sync(1, 128);
+        float* dst0 = p.dw + (long long)(nblk * 64) * p.stride_cout + (long long)(mblk * 64) * 9;
+#pragma unroll 1
+        for (int co = 0; co < 64; ++co) {
+          float* dst = dst0 + (long long)co * p.stride_cout;
+          const float4* src = reinterpret_cast<const float4*>(stg + co * 576);
+          for (int j = L; j < 144; j += 128) {
+            const float4 v = src[j];
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int o = 0; o < p.nops; ++o) {
+          const int tap = p.ops[o].tap[tb];
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            float vals[32];
+            tmem_ld32(acc + (uint32_t)p.ops[o].col + c0, vals);
+            if (tap >= 0 && ci < p.cin_real) {
+              const int te = p.flip ? 8 - tap : tap;
+              float* dst = p.dw + (long long)ci * p.stride_cin + te;
+#pragma unroll
+              for (int n = 0; n < 32; ++n) {
+                const int co = nblk * 64 + c0 + n;
+                if (co < p.cout_real) atomicAdd(dst + (long long)co * p.stride_cout, vals[n]);
+              }
             }
           }
         }
@@ -277,11 +351,9 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
     d.ops[o].tap[1] = pb[o];
   }
   {
-    static int dbg = -1, iss = -1;
+    static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("SRVP_WGRAD_DBG"); dbg = e ? atoi(e) : 0; }
-    if (iss < 0) { const char* e = getenv("SRVP_WGRAD_ISSUERS"); iss = e ? atoi(e) : 1; if (iss != 2) iss = 1; }
     d.dbg = dbg;
-    d.issuers = iss;
     if (dbg & 4) for (int o = 0; o < 5; ++o) d.ops[o].m_lbo = 64 * 8;   // timing only: block-aligned second half (wrong numbers)
   }
   d.dw = a->dw;
