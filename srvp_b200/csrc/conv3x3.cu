@@ -276,12 +276,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     }
   } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop CONVERGED and only the tcgen05 instructions are predicated on one elected lane (elect.sync): inside
+    // a `lane == 0` branch the compiler cannot use the uniform datapath and wraps every MMA in an elect / R2UR.BROADCAST / BRA.U.ANY
+    // loop (~10 extra instructions per MMA), which made the issuing thread -- not the tensor core -- the pace setter of every variant
+    // with N <= 128 (profiles/r03d_wgrad_ablate.log shows the same effect on the weight-gradient kernel). The constant parts of the
+    // descriptors (LBO / SBO / version) are hoisted; per MMA only a 32-bit add on the start-address word remains.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NB, 0, 0);
       uint32_t hit = 0, tcount = 0;
-      int ws = 0;          // weight-ring position and phase, advanced incrementally (no divisions on the issuing thread's critical path)
+      int ws = 0;          // weight-ring position and phase, advanced incrementally
       uint32_t wph = 0;
-      const uint32_t halo_addr = smem_u32(halo), w_addr = smem_u32(wslots);
+      const uint64_t a_const = umma_desc(0, P * 16, 128), b_const = umma_desc(0, NB * 16, 128);
+      const uint32_t a_hi = (uint32_t)(a_const >> 32), b_hi = (uint32_t)(b_const >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_const + (smem_u32(halo) >> 4), b_lo0 = (uint32_t)b_const + (smem_u32(wslots) >> 4);
+      const uint32_t uP = (uint32_t)P;
+      const bool no_mma = (p.dbg & 2) != 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int as = tcount % C::ACC_STAGES;
         mbar_wait(&acc_empty[as], ((tcount / C::ACC_STAGES) & 1) ^ 1);
@@ -292,42 +301,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           const int hs = hit % kHaloStages;
           mbar_wait(&halo_full[hs], (hit / kHaloStages) & 1);
           tc_fence_after();
-          const uint32_t hbase = halo_addr + hs * KCH * P * 16;
-          const uint64_t ad_stage = umma_desc(hbase, P * 16, 128);
+          const uint32_t a_stage = a_lo0 + (uint32_t)hs * (uint32_t)KCH * uP;
           const uint32_t tmask = (TPS == 1 && p.masked) ? p.tap_mask[s] : 0x1ffu;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             if (!((tmask >> tap) & 1u)) continue;  // 4x4 stride-2 family: this (phase, tap) pair has no weight
-            const bool init = fresh;
-            fresh = false;
             if (tap % TPS == 0) {
               mbar_wait(&w_full[ws], wph);
               tc_fence_after();
             }
             const int ky = tap / 3, kx = tap - 3 * ky;
             // descriptors differ only in their start-address field (16-byte units): one base per stage / tap, then plain adds
-            const uint64_t ad_tap = ad_stage + (uint32_t)(ky * p.Wp + kx);
-            const uint64_t bd_tap = umma_desc(w_addr + ws * C::SLOT_BYTES + (tap % TPS) * KCH * NB * 16, NB * 16, 128);
+            const uint32_t a_tap = a_stage + (uint32_t)(ky * p.Wp + kx);
+            const uint32_t b_tap = b_lo0 + (uint32_t)ws * (uint32_t)(C::SLOT_BYTES >> 4) + (uint32_t)(tap % TPS) * (uint32_t)(KCH * NB);
+            const uint32_t acc_first = fresh ? 0u : 1u;
+            if (!no_mma && elect_one_sync()) {
 #pragma unroll
-            for (int mb = 0; mb < C::MBLK; ++mb) {
+              for (int mb = 0; mb < C::MBLK; ++mb) {
 #pragma unroll
-              for (int k = 0; k < KCH / 2; ++k) {
-                if (!(p.dbg & 2)) umma_bf16(acc + mb * NB, ad_tap + (uint32_t)(mb * 128) + (uint32_t)(k * 2) * (uint32_t)P, bd_tap + (uint32_t)(k * 2 * NB), idesc, !(init && k == 0));
+                for (int k = 0; k < KCH / 2; ++k)
+                  umma_bf16_split(acc + mb * NB, a_tap + (uint32_t)(mb * 128) + (uint32_t)(k * 2) * uP, a_hi, b_tap + (uint32_t)(k * 2 * NB), b_hi, idesc,
+                                  k == 0 ? acc_first : 1u);
               }
             }
+            fresh = false;
             if (tap % TPS == TPS - 1) {
-              umma_commit(&w_empty[ws]);
+              if (elect_one_sync()) umma_commit(&w_empty[ws]);
               if (++ws == WS) { ws = 0; wph ^= 1u; }
             }
           }
-          umma_commit(&halo_empty[hs]);
+          if (elect_one_sync()) umma_commit(&halo_empty[hs]);
         }
-        umma_commit(&acc_full[as]);
+        if (elect_one_sync()) umma_commit(&acc_full[as]);
       }
     }
   } else if (warp == 13) {
-    // ------------------------------------------------------------------ weight loader (TMA bulk copies)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ weight loader (TMA bulk copies), converged warp + one elected lane
+    {
       int ws = 0;
       uint32_t wph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -338,8 +348,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           for (int q = 0; q < 9 / TPS; ++q) {
             if (TPS == 1 && !((tmask >> q) & 1u)) continue;
             mbar_wait(&w_empty[ws], wph ^ 1u);
-            mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
-            bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
+              bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
+            }
             if (++ws == WS) { ws = 0; wph ^= 1u; }
           }
         }

@@ -61,24 +61,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
                : "memory");
 }
 
-// One lane of a converged warp (elect.sync).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
-
-// tcgen05.mma with the two 64-bit shared-memory descriptors passed as (low, high) register pairs: the issuing thread updates only the
-// low words (start address) with 32-bit adds.
-__device__ __forceinline__ void umma_bf16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // SWIZZLE_128B canonical layout, MN-major: rows of 128 B (64 channels of one K index); SBO = 8 rows = 1024 B; LBO = stride between
 // 64-channel blocks of the operand (here: between the two fused taps). Fields in 16-byte units.
 __device__ __forceinline__ uint64_t sw128_desc_hi(uint32_t lbo16) {
@@ -180,7 +162,7 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
           uint32_t o16 = off;
 #pragma unroll 1
           for (int k = 0; k < ksteps; ++k) {
-            if (!no_mma && elect_one()) {
+            if (!no_mma && elect_one_sync()) {
 #pragma unroll
               for (int o = 0; o < kMaxOps; ++o) umma_bf16_split(dcol[o], a_lo[o] + o16, a_hi[o], b_lo0 + o16, b_hi, idesc, accf);
             }
@@ -189,10 +171,10 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
           }
           off += sub16;
         }
-        if (elect_one()) umma_commit(&empty[st]);
+        if (elect_one_sync()) umma_commit(&empty[st]);
         if (++st == nstg) { st = 0; ph ^= 1u; }
       }
-      if (elect_one()) umma_commit(acc_full);
+      if (elect_one_sync()) umma_commit(acc_full);
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> shared memory -> coalesced red.add into dW

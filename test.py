@@ -51,6 +51,7 @@ def to_bytes(x):
     return x.mul(255).byte().permute(1, 0, 3, 4, 2).cpu()
 
 
+@torch.no_grad()
 def main(opt):
     if opt.device is None:
         raise RuntimeError('srvp_b200 has no CPU path: pass --device (a CUDA device index)')
@@ -61,7 +62,6 @@ def main(opt):
     if opt.lpips_dir is not None or opt.fvd:
         print('srvp_b200: LPIPS / FVD are outside the hot path (third-party networks); --lpips_dir / --fvd are ignored')
     model, cfg = load_model(opt.xp_dir, opt.model_name, device)
-    torch.set_grad_enabled(False)
     nt_cond = opt.nt_cond if opt.nt_cond is not None else cfg['nt_cond']
     nt_test = opt.nt_gen if opt.nt_gen is not None else (cfg.get('seq_len_test') or cfg['seq_len'])
     dt_train = 1 / cfg['n_euler_steps']
