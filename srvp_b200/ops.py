@@ -23,11 +23,11 @@ def profiled(name):
                 return fn(*args, **kwargs)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _WORK.append([0.0, 0.0, 0.0, None])
+            _WORK.append([0.0, 0.0, 0.0, None, ''])
             out = fn(*args, **kwargs)
             e1.record()
-            fl, by, fx, sub = _WORK.pop()
-            PROFILE.setdefault(name, []).append((e0, e1, fl, by, fx, PROFILE_TAG))
+            fl, by, fx, sub, desc = _WORK.pop()
+            PROFILE.setdefault(name, []).append((e0, e1, fl, by, fx, PROFILE_TAG, desc))
             if sub is not None:      # HBM-bound members of a tensor-bound family, also listed by themselves (bench.py hbm_kernels)
                 PROFILE.setdefault(sub, []).append((e0, e1, fl, by, fx, PROFILE_TAG))
             return out
@@ -40,7 +40,7 @@ def profiled(name):
 _WORK = []
 
 
-def _account(flops=0.0, nbytes=0.0, executed=None, sub=None):
+def _account(flops=0.0, nbytes=0.0, executed=None, sub=None, desc=''):
     """flops: ALGORITHMIC dense count of the reference op this launch stands for; executed: multiply-adds actually
     issued when they differ (per-video split of the skip convolutions); sub: extra profile entry this launch is also listed under."""
     if _WORK:
@@ -49,6 +49,8 @@ def _account(flops=0.0, nbytes=0.0, executed=None, sub=None):
         _WORK[-1][2] += flops if executed is None else executed
         if sub is not None:
             _WORK[-1][3] = sub
+        if desc:
+            _WORK[-1][4] = desc      # one-line description of the launch (tools/step_profile.py)
 
 
 def summarize_profile(profile):
@@ -206,7 +208,8 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
     fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
     # thin operands (first encoder / last decoder layer): HBM-bound, also listed by themselves (bench.py hbm_kernels)
     sub = f'hbm:wgrad_thin[{PROFILE_TAG}]' if min(dz_channels, act_channels) <= 16 else None
-    _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx, sub=sub)
+    _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx, sub=sub,
+             desc=f'F={frames} {H}x{W} act{act_channels} x dz{dz_channels}' + (' map4' if map4 else ''))
     return dw
 
 
@@ -278,7 +281,13 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
         # HBM-bound ends of the network: algorithmic bytes = real input channels read once + output written once
         sub = f'hbm:conv_head_sigmoid[{PROFILE_TAG}]' if sigmoid_nchw else f'hbm:conv_thin_in[{PROFILE_TAG}]'
         nbytes = 2.0 * frames * H * W * cin_real + obytes
-    _account(fx * alg_scale, executed=fx, nbytes=nbytes, sub=sub)
+    desc = ''
+    if PROFILE is not None:
+        modes = '+'.join(('D', 'P', 'U')[s.mode] + str(s.channels) + ('bn' if s.scale is not None else '') + ('fm' if s.frame_map is not None else '')
+                         for s in srcs)
+        desc = (f'F={frames} {H}x{W} in[{modes}] -> {cout}' + (' stats' if stats or stats_out is not None else '') + (' a_out' if save_input else '') +
+                (' add' if add is not None else '') + (' f32out' if out_f32 else '') + (' sigmoid' if sigmoid_nchw else '') + (f' taps{taps}' if taps != 9 else ''))
+    _account(fx * alg_scale, executed=fx, nbytes=nbytes, sub=sub, desc=desc)
     if save_input:
         return out, stats_partial, a_out
     return out, stats_partial
@@ -475,7 +484,8 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
                                         ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
     check(lib().srvp_bn_bwd_apply(ctypes.byref(a), ptr(gamma), ptr(c12[0]), ptr(c12[1]), stream_ptr()), 'bn_bwd_apply')
     n = float(frames * H * W * C)
-    _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0))
+    _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0),
+             desc=f'F={frames} {H}x{W} C={C} da_mode={da_mode}' + (' skip' if skip is not None else '') + (' s2d' if g_s2d else ''))
     return g
 
 
