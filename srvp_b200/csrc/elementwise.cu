@@ -371,6 +371,141 @@ __global__ void __launch_bounds__(256, (MODE == SRVP_SRC_POOL2) ? 1 : 2) bn_bwd_
   }
 }
 
+// Max-pooled case (da at half resolution, routed to the arg-max of each 2x2 window): lean version of bn_bwd_kernel<POOL2>. The generic
+// kernel keeps 40 per-channel constants and two work items in registers (224 registers, one block per SM, ~180 instructions per 16-byte
+// chunk) and ran at 2 TB/s; here the constants live in shared memory (one 16-byte read per channel and item), a thread handles ONE
+// window x 8 channels at a time with the four raw chunks kept packed, and three blocks fit on an SM.
+template <bool APPLY>
+__global__ void __launch_bounds__(256, 3) bn_bwd_pool_kernel(const BnBwdDev p, int items, int items_per_block, const float* __restrict__ gamma,
+                                                            const float* __restrict__ c1, const float* __restrict__ c2) {
+  __shared__ float4 cst[512];                 // per channel: (sc, sh, ka, kb) -- reduce: ka = is, kb = mu*is; apply: see bn_bwd_kernel
+  __shared__ float k0s[APPLY ? 512 : 1];
+  __shared__ float red[APPLY ? 1 : 256 * 17];
+  const int tid = threadIdx.x;
+  for (int c = tid; c < p.C; c += 256) {
+    const float is = p.invstd[c], mu = p.mean[c];
+    float4 v;
+    v.x = p.scale[c]; v.y = p.shift[c];
+    if (APPLY) {
+      const float k0 = gamma[c] * is;
+      k0s[c] = k0;
+      v.z = -is * k0 * c2[c];
+      v.w = k0 * (mu * is * c2[c] - c1[c]);
+    } else {
+      v.z = is; v.w = mu * is;
+    }
+    cst[c] = v;
+  }
+  __syncthreads();
+  const int cpp = p.C / 8;
+  const int j = tid % cpp, lanes = 256 / cpp, pl = tid / cpp, c0 = j * 8;
+  const int Hi = p.H >> 1, Wi = p.W >> 1;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+  const int i0 = blockIdx.x * items_per_block;
+  const int i1 = min(items, i0 + items_per_block);
+  const size_t zrow = (size_t)p.W * p.C;
+  for (int it = i0 + pl; it < i1; it += lanes) {
+    const unsigned t2 = (unsigned)it / (unsigned)Wi;
+    const int xi = (int)((unsigned)it - t2 * (unsigned)Wi);
+    const int f = (int)(t2 / (unsigned)Hi);
+    const int yi = (int)(t2 - (unsigned)f * (unsigned)Hi);
+    const __nv_bfloat16* zb = p.z + (((size_t)f * p.H + 2 * yi) * p.W + 2 * xi) * p.C + c0;
+    uint4 zr[4];
+    zr[0] = __ldg(reinterpret_cast<const uint4*>(zb));
+    zr[1] = __ldg(reinterpret_cast<const uint4*>(zb + p.C));
+    zr[2] = __ldg(reinterpret_cast<const uint4*>(zb + zrow));
+    zr[3] = __ldg(reinterpret_cast<const uint4*>(zb + zrow + p.C));
+    const uint4 dr = __ldg(reinterpret_cast<const uint4*>(p.da + (((size_t)f * Hi + yi) * Wi + xi) * p.da_cpitch + p.da_coff + c0));
+    const int b = p.inv_map ? __ldg(p.inv_map + f) : -1;
+    uint4 sk[4];
+    if (b >= 0) {      // this frame feeds the skip connection: its gradient (already summed over time, nt == 1 checked on the host) adds at full resolution
+      const __nv_bfloat16* sb = p.skip + (((size_t)b * p.H + 2 * yi) * p.W + 2 * xi) * p.skip_cpitch + p.skip_coff + c0;
+      const size_t srow = (size_t)p.W * p.skip_cpitch;
+      sk[0] = __ldg(reinterpret_cast<const uint4*>(sb));
+      sk[1] = __ldg(reinterpret_cast<const uint4*>(sb + p.skip_cpitch));
+      sk[2] = __ldg(reinterpret_cast<const uint4*>(sb + srow));
+      sk[3] = __ldg(reinterpret_cast<const uint4*>(sb + srow + p.skip_cpitch));
+    }
+    uint32_t outw[4][4];   // apply: packed results of the four positions
+    const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dr);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {        // channel pairs
+      float o[4][2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const int e = 2 * h + l;
+        const float4 cc = cst[c0 + e];
+        float zq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t w = reinterpret_cast<const uint32_t*>(&zr[q])[h];
+          zq[q] = __uint_as_float(l ? (w & 0xffff0000u) : (w << 16));
+        }
+        const float da = __uint_as_float(l ? (dw[h] & 0xffff0000u) : (dw[h] << 16));
+        // arg-max of the pooled activation = arg-max (scale >= 0) / arg-min (scale < 0) of the raw values, first extremum wins
+        const float sg = cc.x >= 0.f ? 1.f : -1.f;
+        int am = 0;
+        float best = sg * zq[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const float v = sg * zq[q];
+          if (v > best) { best = v; am = q; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float g = (am == q) ? da : 0.f;
+          if (b >= 0) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(&sk[q])[h];
+            g += __uint_as_float(l ? (w & 0xffff0000u) : (w << 16));
+          }
+          const float pre = fmaf(zq[q], cc.x, cc.y);
+          const float gg = (p.lrelu && !(pre > 0.f)) ? 0.2f * g : g;
+          if (APPLY) {
+            o[q][l] = fmaf(k0s[c0 + e], gg, fmaf(zq[q], cc.z, cc.w));
+          } else {
+            s1[e] += gg;
+            s2[e] = fmaf(gg, fmaf(zq[q], cc.z, -cc.w), s2[e]);
+          }
+        }
+      }
+      if (APPLY) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) outw[q][h] = pack_bf16x2(o[q][0], o[q][1]);
+      }
+    }
+    if (APPLY) {
+      __nv_bfloat16* gb = p.g + (((size_t)f * p.H + 2 * yi) * p.W + 2 * xi) * p.C + c0;
+      *reinterpret_cast<uint4*>(gb) = make_uint4(outw[0][0], outw[0][1], outw[0][2], outw[0][3]);
+      *reinterpret_cast<uint4*>(gb + p.C) = make_uint4(outw[1][0], outw[1][1], outw[1][2], outw[1][3]);
+      *reinterpret_cast<uint4*>(gb + zrow) = make_uint4(outw[2][0], outw[2][1], outw[2][2], outw[2][3]);
+      *reinterpret_cast<uint4*>(gb + zrow + p.C) = make_uint4(outw[3][0], outw[3][1], outw[3][2], outw[3][3]);
+    }
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { red[tid * 17 + e] = s1[e]; red[tid * 17 + 8 + e] = s2[e]; }
+    __syncthreads();
+    if (tid < cpp) {
+      float a1[8], a2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        const float* r = red + (l * cpp + tid) * 17;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a1[e] += r[e]; a2[e] += r[8 + e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float* dst = p.partial + ((size_t)blockIdx.x * p.C + tid * 8 + e) * 2;
+        dst[0] = a1[e];
+        dst[1] = a2[e];
+      }
+    }
+  }
+}
+
 // Fast path of the same two passes for the plain case (DIRECT da with the layer's own geometry, no skip gradient, dense output):
 // the tensors are flat arrays of 16-byte chunks, a thread keeps ONE channel chunk for its whole grid-stride loop, so there is no
 // per-item index arithmetic beyond one add (the general kernel spends ~180 instructions per chunk, this one ~70).
@@ -809,6 +944,11 @@ static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gam
   SRVP_REQUIRE(items * 4 < 2000000000LL, "bn_bwd: problem too large for 32-bit pixel indices");
   const int nb = bn_bwd_blocks(items, a->C, a->da_mode);
   const int ipb = (int)((items + nb - 1) / nb);
+  if (pooled && a->C <= 512 && !a->g_s2d && (a->skip == nullptr || a->nt == 1)) {
+    if (apply) bn_bwd_pool_kernel<true><<<nb, 256, 0, st>>>(d, (int)items, ipb, gamma, c1, c2);
+    else bn_bwd_pool_kernel<false><<<nb, 256, 0, st>>>(d, (int)items, ipb, nullptr, nullptr, nullptr);
+    return check_launch(apply ? "bn_bwd_apply" : "bn_bwd_reduce");
+  }
 #define SRVP_BN_LAUNCH(MODE)                                                                    \
   if (apply) bn_bwd_kernel<MODE, true><<<nb, 256, 0, st>>>(d, (int)items, ipb, gamma, c1, c2);       \
   else bn_bwd_kernel<MODE, false><<<nb, 256, 0, st>>>(d, (int)items, ipb, nullptr, nullptr, nullptr);

@@ -169,6 +169,43 @@ def test_bn_lrelu_pool_backward(dev, mode, with_skip, C, H):
     assert rel(dg, gamma.grad) < 1e-3 and rel(db, beta.grad) < 1e-3
 
 
+@pytest.mark.parametrize('C,H,with_skip', [(64, 16, True), (512, 8, True), (256, 8, False), (128, 32, True)])
+def test_bn_pooled_backward_lean_kernel(dev, C, H, with_skip):
+    """bn_bwd_pool_kernel (max-pooled consumer, skip gradient already summed over time: nt = 1 as the per-video split of the decoder
+    produces it) against autograd of BatchNorm2d(train) -> LeakyReLU -> MaxPool2d, plus the skip consumer on selected frames."""
+    from srvp_b200 import ops
+    Fr, W, B = 7, H, 3
+    torch.manual_seed(C + H)
+    z = torch.randn(Fr, H, W, C, device=dev).to(torch.bfloat16)
+    gamma = (torch.rand(C, device=dev) + 0.5)
+    gamma[::3] *= -1                                   # negative scales: arg-MIN routing
+    gamma.requires_grad_(True)
+    beta = (torch.randn(C, device=dev) * 0.2).requires_grad_(True)
+    zf = z.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    a = F.leaky_relu(F.batch_norm(zf, None, None, gamma, beta, True, 0.0, 1e-5), 0.2)
+    out = F.max_pool2d(a, 2)
+    da = (torch.randn_like(out) * 0.1).to(torch.bfloat16)
+    bn = _BN()
+    bn.weight, bn.bias = gamma.detach(), beta.detach()
+    st = ops.BNState(C, dev)
+    ops.bn_finalize(ops.channel_stats(z.view(-1, C)), float(Fr * H * W), bn, st, training_update=False)
+    loss = (out * da.float()).sum()
+    skip, inv = None, None
+    if with_skip:
+        skip = (torch.randn(B, H, W, C + 64, device=dev) * 0.1).to(torch.bfloat16)
+        inv = torch.full((Fr,), -1, dtype=torch.int32, device=dev)
+        sel = [1, 4, 6]
+        for v, f in enumerate(sel):
+            inv[f] = v
+            loss = loss + (a[f] * skip[v, ..., 64:].float().permute(2, 0, 1)).sum()
+    loss.backward()
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dz = ops.bn_bwd(z, st, gamma.detach(), dg, db, da.permute(0, 2, 3, 1).contiguous(), 1, Fr, H, W, C, skip=skip, skip_coff=64, nt=1, B=B,
+                    inv_map=inv)
+    assert rel(dz.float(), zf.grad.permute(0, 2, 3, 1)) < 5e-3
+    assert rel(dg, gamma.grad) < 1e-3 and rel(db, beta.grad) < 1e-3
+
+
 def test_bn_finalize_statistics_and_running_update(dev):
     from srvp_b200 import ops
     C, rows = 96, 5000
