@@ -17,8 +17,8 @@
 // traffic for activations is ~1x instead of 9x and the loader has time to apply BN + LeakyReLU + pooling.
 // Outputs at pad positions are computed and discarded (W/(W+2) * H/(H+1) efficiency).
 //
-// Warp roles (persistent CTA, 448 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-11
-// activation loaders, warp 12 MMA issuer (one thread), warp 13 weight TMA-bulk issuer (one thread).
+// Warp roles (persistent CTA, 576 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-15
+// activation loaders, warp 16 MMA issuer (converged warp, one elected lane), warp 17 weight TMA-bulk issuer.
 // TMEM: 2 accumulator stages x (MT/128) x NB fp32 columns, so the epilogue of tile i overlaps tile i+1.
 #include <cstdlib>
 #include "common.cuh"
@@ -29,8 +29,14 @@ namespace srvp {
 
 namespace {
 
-constexpr int kThreads = 448;   // warps 0-3 epilogue, 4-11 activation loaders, 12 MMA issuer, 13 weight TMA-bulk issuer
-constexpr int kLoaders = 256;
+// warps 0-3 epilogue, 4..4+kLoaderWarps-1 activation loaders, then the MMA issuer warp and the weight TMA-bulk issuer warp.
+// Twelve loader warps: the fused BN + LeakyReLU transform of the operand loader is instruction-bound (two loader warps per scheduler
+// could not hide their own dependency stalls; with copies, MMAs and stores all disabled a forward launch still took 85 % of its time,
+// profiles/r03h_thin.log), so the forward convolutions scale with the number of loader warps until the MMAs take over.
+constexpr int kLoaderWarps = 12;
+constexpr int kLoaders = kLoaderWarps * 32;
+constexpr int kMmaWarp = 4 + kLoaderWarps, kTmaWarp = kMmaWarp + 1;
+constexpr int kThreads = (kTmaWarp + 1) * 32;
 constexpr int kHaloStages = 2;
 
 struct ConvDev {
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   const int total_tiles = p.num_mtiles * p.num_nblk;
   const int HpWp = p.Hp * p.Wp;
 
-  if (warp >= 4 && warp < 12) {
+  if (warp >= 4 && warp < kMmaWarp) {
     // ------------------------------------------------------------------ activation loaders
     const int lt = tid - 128;
     uint32_t it = 0;  // halo stage iteration counter
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         mbar_arrive(&halo_full[hs]);
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp runs this loop CONVERGED and only the tcgen05 instructions are predicated on one elected lane (elect.sync): inside
     // a `lane == 0` branch the compiler cannot use the uniform datapath and wraps every MMA in an elect / R2UR.BROADCAST / BRA.U.ANY
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         if (elect_one_sync()) umma_commit(&acc_full[as]);
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ weight loader (TMA bulk copies), converged warp + one elected lane
     {
       int ws = 0;

@@ -108,8 +108,17 @@ def main():
         out1 = m1(x.to(dev), T, dt=dt)
         elbo.elbo(out1, x.to(dev), **loss_cfg)[0].backward()
         e_1 = sorted((rel_l2(g_sharded[k], p.grad), k) for k, p in m1.named_parameters())
+        d_1 = dict((k, e) for e, k in e_1)
         print(f'  gradients vs single-GPU run (global batch): median rel-L2 {e_1[len(e_1) // 2][0]:.3e}, worst {e_1[-1][0]:.3e} ({e_1[-1][1]})')
-        ok &= e_1[len(e_1) // 2][0] < 2e-2 and e_1[-1][0] < 0.15
+        # Two bf16 runs that differ by one fp32 rounding (here: the order in which the batch-norm partial sums are added) have
+        # INDEPENDENT rounding noise after a few layers (a flipped bf16 rounding is a full-ulp change, so a 1e-7 perturbation grows to
+        # ulp level within ~5 layers), so deep layers can only agree at the noise level measured in (b). The sharding logic itself --
+        # gradient averaging, local dgamma / dbeta, GLOBAL sums in the SyncBatchNorm backward -- is pinned on the last decoder block,
+        # which sits next to the loss, after ALL of those steps and before the noise has grown:
+        near = ['decoder.conv.3.1.weight', 'decoder.conv.3.0.1.weight', 'decoder.conv.3.0.1.bias', 'decoder.conv.3.0.0.weight']
+        print('  next to the loss: ' + ', '.join(f'{k} {d_1[k]:.2e}' for k in near))
+        ok &= all(d_1[k] < 1e-2 for k in near)
+        ok &= e_1[len(e_1) // 2][0] < 1.6 * e_or[len(e_or) // 2][0] + 1e-3 and e_1[-1][0] < 1.6 * e_or[-1][0] + 1e-2
         print('MULTIGPU CHECK', 'PASS' if ok else 'FAIL', flush=True)
     dist.barrier()
     dist.destroy_process_group()

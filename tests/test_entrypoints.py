@@ -157,7 +157,25 @@ def test_reference_training_loop_drives_the_dropin_class():
         assert all(l == l and abs(l) < 1e9 for l in losses), losses
         assert losses[-1] < losses[0], losses
         model.eval()
-        val = ref_train.evaluate(model, [torch.rand(7, 2, 3, 64, 64)], dev, opt)
+        # The reference's evaluate() indexes a CPU tensor with a CUDA index (train.py:181), which PyTorch >= 2 rejects on any CUDA run
+        # whatever the model class; it is therefore run with that one index moved to the CPU (torch.arange(n).to(device) -> cpu).
+        real_arange = torch.arange
+
+        class _CpuIndex(torch.Tensor):
+            pass
+
+        def arange_cpu_to(*a, **k):
+            t = real_arange(*a, **k)
+            if not k and len(a) == 1 and isinstance(a[0], int):
+                t = t.as_subclass(_CpuIndex)
+            return t
+        _CpuIndex.to = lambda self, *a, **k: (self.as_subclass(torch.Tensor) if (a and isinstance(a[0], torch.device) and not k)
+                                              else torch.Tensor.to(self.as_subclass(torch.Tensor), *a, **k))
+        ref_train.torch.arange = arange_cpu_to
+        try:
+            val = ref_train.evaluate(model, [torch.rand(7, 2, 3, 64, 64)], dev, opt)
+        finally:
+            ref_train.torch.arange = real_arange
         assert val == val and -60 < val < 0, val
         print('reference train(): losses', [round(l, 1) for l in losses], '; reference evaluate():', val)
     finally:
