@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmDev p) 
       mbar_arrive(&full[st]);
     }
   } else if (warp == 8) {
-    if (lane == 0 && nsteps > 0) {
+    if (nsteps > 0) {   // converged warp, one elected lane issues (see conv3x3.cu)
       const uint32_t idesc = umma_idesc_bf16(BM, BN, a_kmajor ? 0 : 1, b_kmajor ? 0 : 1);
       const uint32_t base = smem_u32(smem);
       for (int i = 0; i < nsteps; ++i) {
@@ -128,15 +128,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmDev p) 
         mbar_wait(&full[st], (i / GSTAGES) & 1);
         tc_fence_after();
         const uint32_t ta = base + st * 2 * OP_BYTES, tb = ta + OP_BYTES;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t ad = a_kmajor ? umma_desc(ta + kk * 2 * 2048, 2048, 128) : umma_desc(ta + kk * 256, 128, 1024);
-          const uint64_t bd = b_kmajor ? umma_desc(tb + kk * 2 * 2048, 2048, 128) : umma_desc(tb + kk * 256, 128, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (i | kk) != 0);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ad = a_kmajor ? umma_desc(ta + kk * 2 * 2048, 2048, 128) : umma_desc(ta + kk * 256, 128, 1024);
+            const uint64_t bd = b_kmajor ? umma_desc(tb + kk * 2 * 2048, 2048, 128) : umma_desc(tb + kk * 256, 128, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (i | kk) != 0);
+          }
+          umma_commit(&empty[st]);
         }
-        umma_commit(&empty[st]);
       }
-      umma_commit(acc_full);
+      if (elect_one_sync()) umma_commit(acc_full);
     }
   } else if (nsteps > 0) {
     mbar_wait(acc_full, 0);

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kLatThreads, 1) latent_fwd_kernel(const LatFwd
 
   if (warp == 4) {
     // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
+    {   // converged warp: only the asynchronous instructions are predicated on one elected lane (see conv3x3.cu)
       uint32_t it = 0;
       for_each_mlp(p, [&](const MlpDev& m, bool, int) {
         for (int l = 0; l < m.nl; ++l) {
@@ -115,15 +115,17 @@ __global__ void __launch_bounds__(kLatThreads, 1) latent_fwd_kernel(const LatFwd
           for (int t = 0; t < ntiles; ++t, ++it) {
             const int sl = it % kWSlots;
             mbar_wait(&R.w_empty[sl], ((it / kWSlots) & 1) ^ 1);
-            mbar_arrive_expect_tx(&R.w_full[sl], kTileBytes);
-            bulk_g2s(wring + (size_t)sl * kTileBytes, src + (size_t)t * kTileBytes, kTileBytes, &R.w_full[sl]);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&R.w_full[sl], kTileBytes);
+              bulk_g2s(wring + (size_t)sl * kTileBytes, src + (size_t)t * kTileBytes, kTileBytes, &R.w_full[sl]);
+            }
           }
         }
       });
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {   // converged warp
       constexpr uint32_t idesc = umma_idesc_bf16(128, NV, 0, 0);
       uint32_t it = 0, xphase = 0, hsel = 0;
       const uint32_t wbase = smem_u32(wring);
@@ -141,11 +143,13 @@ __global__ void __launch_bounds__(kLatThreads, 1) latent_fwd_kernel(const LatFwd
               tc_fence_after();
               const uint64_t ad0 = umma_desc(wbase + sl * kTileBytes, 128 * 16, 128);
               const uint64_t bd0 = umma_desc(xaddr + ks * 8 * NV * 16, NV * 16, 128);
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mb * NV, ad0 + k * (2 * 128 * 16 / 16), bd0 + k * (2 * NV * 16 / 16), idesc, (ks | k) != 0);
-              umma_commit(&R.w_empty[sl]);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mb * NV, ad0 + k * (2 * 128 * 16 / 16), bd0 + k * (2 * NV * 16 / 16), idesc, (ks | k) != 0);
+                umma_commit(&R.w_empty[sl]);
+              }
             }
-            umma_commit(&R.acc_full[mb]);
+            if (elect_one_sync()) umma_commit(&R.acc_full[mb]);
           }
           if (l < m.nl - 1) hsel ^= 1;  // hidden layers alternate between the two buffers
         }
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kLatThreads, 1) latent_bwd_kernel(const LatBwd
   const int S = p.os * (p.nt - 1);
 
   if (warp == 4) {
-    if (lane == 0) {
+    {   // converged warp
       uint32_t it = 0;
       for_each_mlp_bwd(p, [&](const MlpDev& m, bool, int) {
         for (int l = 0; l < m.nl; ++l) {
@@ -327,14 +331,16 @@ __global__ void __launch_bounds__(kLatThreads, 1) latent_bwd_kernel(const LatBwd
           for (int t = 0; t < ntiles; ++t, ++it) {
             const int sl = it % kWSlots;
             mbar_wait(&R.w_empty[sl], ((it / kWSlots) & 1) ^ 1);
-            mbar_arrive_expect_tx(&R.w_full[sl], kTileBytes);
-            bulk_g2s(wring + (size_t)sl * kTileBytes, src + (size_t)t * kTileBytes, kTileBytes, &R.w_full[sl]);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&R.w_full[sl], kTileBytes);
+              bulk_g2s(wring + (size_t)sl * kTileBytes, src + (size_t)t * kTileBytes, kTileBytes, &R.w_full[sl]);
+            }
           }
         }
       });
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {   // converged warp
       constexpr uint32_t idesc = umma_idesc_bf16(128, NV, 0, 0);
       uint32_t it = 0, xphase = 0, hsel = 0;
       const uint32_t wbase = smem_u32(wring);
@@ -352,11 +358,13 @@ __global__ void __launch_bounds__(kLatThreads, 1) latent_bwd_kernel(const LatBwd
               tc_fence_after();
               const uint64_t ad0 = umma_desc(wbase + sl * kTileBytes, 128 * 16, 128);
               const uint64_t bd0 = umma_desc(xaddr + ks * 8 * NV * 16, NV * 16, 128);
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mb * NV, ad0 + k * 256, bd0 + k * (2 * NV), idesc, (ks | k) != 0);
-              umma_commit(&R.w_empty[sl]);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mb * NV, ad0 + k * 256, bd0 + k * (2 * NV), idesc, (ks | k) != 0);
+                umma_commit(&R.w_empty[sl]);
+              }
             }
-            umma_commit(&R.acc_full[mb]);
+            if (elect_one_sync()) umma_commit(&R.acc_full[mb]);
           }
           if (l < m.nl - 1) hsel ^= 1;
         }

@@ -189,31 +189,38 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
   } else if (warp >= 12) {
     // ------------------------------------------------------------------ MMA issuers: warps 12 and 13 share this CTA's taps
     // (one thread sustains ~1 MMA / 50 cycles, the tensor core accepts one small-N MMA per 40: two issuers close the gap)
-    if (lane == 0 && nsteps > 0) {
+    // both issuer warps run their loops CONVERGED, only the tcgen05 instructions are predicated on one elected lane (see conv3x3.cu:
+    // inside a `lane == 0` branch every MMA is wrapped in an elect / broadcast loop); descriptor words that do not change are hoisted
+    if (nsteps > 0) {
       const int half = (ntaps + 1) / 2;
       const int tap_lo = tap0 + (warp == 12 ? 0 : half), tap_hi = tap0 + (warp == 12 ? half : ntaps);
       constexpr uint32_t idesc = umma_idesc_bf16(128, NBc, 1, 1);
-      const uint32_t base = smem_u32(smem);
+      const uint32_t base16 = smem_u32(smem) >> 4;
+      const uint64_t a_const = umma_desc(0, 128, m_rows * 16), b_const = umma_desc(0, 128, n_rows * 16);
+      const uint32_t a_hi = (uint32_t)(a_const >> 32), b_hi = (uint32_t)(b_const >> 32);
+      const uint32_t a_lo_c = (uint32_t)a_const, b_lo_c = (uint32_t)b_const;
+      const uint32_t stage16 = (uint32_t)(stage_bytes >> 4), m16 = (uint32_t)(m_bytes >> 4);
+      const bool no_mma = (p.dbg & 3) == 2;
       for (int i = 0; i < nsteps; ++i) {
         const int st = i % kStages;
         mbar_wait(&full[st], (i / kStages) & 1);
         if (!(p.dbg & 4)) fence_proxy_async_smem();  // cp.async (generic proxy) writes of the copy warps -> visible to the UMMA (async proxy) reads
         tc_fence_after();
-        const uint32_t ma = base + st * stage_bytes, na = ma + m_bytes;
-        const uint64_t ad0 = umma_desc(ma, 128, m_rows * 16), bd0 = umma_desc(na, 128, n_rows * 16);
+        const uint32_t ma = a_lo_c + base16 + (uint32_t)st * stage16, na = b_lo_c + base16 + (uint32_t)st * stage16 + m16;
 #pragma unroll 1
         for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int ky = tap / 3, kx = tap - 3 * ky;
           const uint32_t shift = (uint32_t)(ky * p.Wp + kx);  // in 16-byte units = descriptor address units
-          const uint64_t ad = ad0 + (p.halo_on_m ? shift : 0u), bd = bd0 + (p.halo_on_m ? 0u : shift);
+          const uint32_t ad = ma + (p.halo_on_m ? shift : 0u), bd = na + (p.halo_on_m ? 0u : shift);
+          const uint32_t dcol = tmem_base + (uint32_t)((tap - tap0) * NBc);
+          if (!no_mma && elect_one_sync()) {
 #pragma unroll
-          for (int kk = 0; kk < PT / 16; ++kk) {
-            if ((p.dbg & 3) != 2) umma_bf16(tmem_base + (tap - tap0) * NBc, ad + kk * 16, bd + kk * 16, idesc, (i | kk) != 0);
+            for (int kk = 0; kk < PT / 16; ++kk) umma_bf16_split(dcol, ad + kk * 16, a_hi, bd + kk * 16, b_hi, idesc, (i | kk) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&empty[st]);
+        if (elect_one_sync()) umma_commit(&empty[st]);
       }
-      umma_commit(acc_full);
+      if (elect_one_sync()) umma_commit(acc_full);
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> red.add into dW
