@@ -394,6 +394,17 @@ int srvp_latent_bwd(const srvp_latent_bwd_args* args, void* stream);
 int srvp_colsum(const void* in, int32_t dtype, int64_t rows, int32_t cols, int64_t ld, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Decoder head (VGG64Decoder, module/conv.py:352-354 + :273-274): x_hat = sigmoid(ConvTranspose2d(64 -> nc, 3, 1, 1)(lrelu(bn(z)))) in one
+ * kernel for 64x64 images -- the HBM-bound end of the decoder. z: (frames, 64, 64, 64) raw bf16 output of the last block with its
+ * batch-norm affine (scale / shift, NULL = identity), weight: the nn.ConvTranspose2d parameter (64, nc, 3, 3) fp32 (packed in the
+ * kernel), xhat: (frames, nc, 64, 64) fp32. a_out (optional, training): the activated input (frames, 64, 64, 64) bf16 for
+ * srvp_wgrad3x3. The convolution is evaluated tap-expanded on the tensor core (D[pixel][(tap, co)], one 128 x 32 x 64 GEMM block per
+ * 128 pixels) and the 3x3 stencil is a shared-memory gather in the epilogue (csrc/head.cu).
+ * ---------------------------------------------------------------------------------------------- */
+int srvp_decoder_head_fwd(const srvp_bf16* z, const float* scale, const float* shift, int32_t lrelu, const float* weight, int32_t frames,
+                          int32_t H, int32_t W, int32_t cin, int32_t nc, float* xhat, srvp_bf16* a_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Evaluation metrics of the rollout path, one launch for both:
  *   out_mse[p]  = mean over the plane of (clamp(pred) - target)^2          (test.py:249: F.mse_loss(...).mean([3, 4]); PSNR = 10 log10(1/mse))
  *   out_ssim[p] = mean of the SSIM map of the plane                         (test.py:251 _ssim_wrapper -> metrics/ssim.py:81-111: 11x11 Gaussian

@@ -120,7 +120,7 @@ EXPORTS = [
     'srvp_peer_bn_buffer_bytes', 'srvp_peer_alloc', 'srvp_peer_open', 'srvp_peer_close', 'srvp_bn_finalize_p2p', 'srvp_bn_bwd_finalize_p2p',
     'srvp_nll_fwd', 'srvp_nll_bwd', 'srvp_kl_normal_fwd', 'srvp_l2_rows_fwd', 'srvp_scale_by_scalar_f32',
     'srvp_linear_f32', 'srvp_act_bwd_f32', 'srvp_lstm_fwd', 'srvp_lstm_bwd',
-    'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum', 'srvp_psnr_ssim',
+    'srvp_pack_linear_size', 'srvp_pack_linear', 'srvp_latent_fwd', 'srvp_latent_bwd', 'srvp_colsum', 'srvp_psnr_ssim', 'srvp_decoder_head_fwd',
 ]
 
 

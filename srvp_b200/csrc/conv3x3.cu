@@ -17,8 +17,8 @@
 // traffic for activations is ~1x instead of 9x and the loader has time to apply BN + LeakyReLU + pooling.
 // Outputs at pad positions are computed and discarded (W/(W+2) * H/(H+1) efficiency).
 //
-// Warp roles (persistent CTA, 576 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-15
-// activation loaders, warp 16 MMA issuer (converged warp, one elected lane), warp 17 weight TMA-bulk issuer.
+// Warp roles (persistent CTA, 704 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-19
+// activation loaders, warp 20 MMA issuer (converged warp, one elected lane), warp 21 weight TMA-bulk issuer.
 // TMEM: 2 accumulator stages x (MT/128) x NB fp32 columns, so the epilogue of tile i overlaps tile i+1.
 #include <cstdlib>
 #include "common.cuh"
@@ -30,10 +30,10 @@ namespace srvp {
 namespace {
 
 // warps 0-3 epilogue, 4..4+kLoaderWarps-1 activation loaders, then the MMA issuer warp and the weight TMA-bulk issuer warp.
-// Twelve loader warps: the fused BN + LeakyReLU transform of the operand loader is instruction-bound (two loader warps per scheduler
+// Sixteen loader warps: the fused BN + LeakyReLU transform of the operand loader is instruction-bound (two loader warps per scheduler
 // could not hide their own dependency stalls; with copies, MMAs and stores all disabled a forward launch still took 85 % of its time,
 // profiles/r03h_thin.log), so the forward convolutions scale with the number of loader warps until the MMAs take over.
-constexpr int kLoaderWarps = 12;
+constexpr int kLoaderWarps = 16;
 constexpr int kLoaders = kLoaderWarps * 32;
 constexpr int kMmaWarp = 4 + kLoaderWarps, kTmaWarp = kMmaWarp + 1;
 constexpr int kThreads = (kTmaWarp + 1) * 32;
@@ -371,6 +371,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mtile = tile / p.num_nblk, nblk = tile % p.num_nblk;
       const int as = tcount % C::ACC_STAGES;
+      if constexpr (EPI == SRVP_EPI_RAW_BF16) {
+        if (p.add != nullptr) {
+          // the per-video addend is read row by row by the thread that owns the row (128 contiguous bytes per 32 columns): pull this
+          // tile's rows into L2 while the MMAs of the tile are still running, otherwise every batch exposes a full HBM round trip on the
+          // epilogue's critical path (+1.06 ms on the 64-channel 64x64 layer, profiles/r03k_fwd_ablate.log)
+#pragma unroll 1
+          for (int mb = 0; mb < C::MBLK; ++mb) {
+            const long long v = (long long)mtile * MT + mb * 128 + tid;
+            int f = 0, y = 0, x = 0;
+            if (decode_vpix(v, p.vtotal, HpWp, p.Wp, p.H, p.W, f, y, x)) {
+              const float* ap = p.add + ((size_t)(((f % p.add_frames) * p.H + y) * p.W + x)) * p.cout + nblk * NB;
+#pragma unroll
+              for (int b = 0; b < NB * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ap) + b));
+            }
+          }
+        }
+      }
       mbar_wait(&acc_full[as], (tcount / C::ACC_STAGES) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);

@@ -335,10 +335,14 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
         prev = Src(z, blk.cout, st.scale, st.shift, None, 0, SRC_DIRECT, True)
     final = dec.conv[3][1]
     c.final_src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, SRC_DIRECT, True)
-    wp = ops.pack_conv3x3(final.weight, 'convT')
-    r = ops.conv3x3([c.final_src], wp, F_, 64, 64, final.out_channels, sigmoid_nchw=True, save_input=training)
-    c.x_hat = r[0]
-    c.final_a = r[2] if training else None
+    if final.in_channels == 64 and final.out_channels <= 3 and tuple(prev.tensor.shape[1:]) == (64, 64, 64):
+        # dedicated head kernel (csrc/head.cu): activation + tap-expanded 64 -> nc transposed convolution + sigmoid
+        c.x_hat, c.final_a = ops.decoder_head_fwd(c.final_src, final.weight, F_, final.out_channels, save_input=training)
+    else:
+        wp = ops.pack_conv3x3(final.weight, 'convT')
+        r = ops.conv3x3([c.final_src], wp, F_, 64, 64, final.out_channels, sigmoid_nchw=True, save_input=training)
+        c.x_hat = r[0]
+        c.final_a = r[2] if training else None
     if training and want_stats_update:
         torch._foreach_add_([b.num_batches_tracked for b in _bn_list(dec)], 1)
     return c.x_hat, c

@@ -293,6 +293,23 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
     return out, stats_partial
 
 
+@profiled('decoder_head')
+def decoder_head_fwd(src, weight, frames, nc, save_input=False):
+    """x_hat = sigmoid(ConvTranspose2d(64 -> nc, 3, 1, 1)(activated src)) for 64x64 images (csrc/head.cu). src: a DIRECT Src over the raw
+    (frames, 64, 64, 64) bf16 output of the last decoder block. Returns (x_hat (frames, nc, 64, 64) fp32, a_out or None)."""
+    z = src.tensor
+    assert src.mode == _lib.SRC_DIRECT and src.frame_map is None and src.coff == 0 and z.shape[-1] == 64 and src.channels == 64
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and tuple(weight.shape) == (64, nc, 3, 3)
+    xhat = torch.empty(frames, nc, 64, 64, dtype=torch.float32, device=z.device)
+    a_out = torch.empty(frames, 64, 64, 64, dtype=torch.bfloat16, device=z.device) if save_input else None
+    check(lib().srvp_decoder_head_fwd(ptr(z), ptr(src.scale), ptr(src.shift), c_int(int(src.lrelu)), ptr(weight), c_int(frames), c_int(64), c_int(64),
+                                      c_int(64), c_int(nc), ptr(xhat), ptr(a_out), stream_ptr()), 'decoder_head_fwd')
+    nbytes = 2.0 * frames * 4096 * 64 + 4.0 * xhat.numel()
+    _account(2.0 * frames * 4096 * 64 * nc * 9, nbytes, sub=f'hbm:conv_head_sigmoid[{PROFILE_TAG}]',
+             desc=f'F={frames} 64x64 in[D64bn] -> {nc} sigmoid (tap-expanded)' + (' a_out' if save_input else ''))
+    return xhat, a_out
+
+
 def conv3x3_stats_rows(frames, H, W, cout, kin_total):
     """Rows of the per-CTA statistics a conv3x3 launch of this geometry writes."""
     return lib().srvp_conv3x3_num_mtiles(c_int(frames), c_int(H), c_int(W), c_int(padded_n(cout)), c_int(kin_total))

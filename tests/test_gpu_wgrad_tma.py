@@ -135,3 +135,26 @@ def test_psnr_ssim_kernel_matches_reference_formula(dev):
             assert torch.allclose(psnr[s], r_psnr, atol=1e-4, rtol=1e-5)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize('nc,frames,bn', [(3, 5, True), (1, 3, True), (3, 2, False)])
+def test_decoder_head_kernel_matches_torch(dev, nc, frames, bn):
+    """srvp_decoder_head_fwd (activation + tap-expanded transposed convolution + sigmoid) against torch on identical bf16 operands, and
+    against the generic conv3x3 kernel's sigmoid epilogue; the activated copy it writes must equal the loader's."""
+    from srvp_b200 import ops
+    torch.manual_seed(nc * 10 + frames)
+    z = torch.randn(frames, 64, 64, 64, device=dev).to(torch.bfloat16)
+    sc = (torch.rand(64, device=dev) + 0.5) * torch.where(torch.rand(64, device=dev) < 0.2, -1.0, 1.0) if bn else None
+    sh = torch.randn(64, device=dev) * 0.3 if bn else None
+    w = torch.randn(64, nc, 3, 3, device=dev) * 0.1
+    src = ops.Src(z, 64, sc, sh, None, 0, 0, True)
+    xh, a_out = ops.decoder_head_fwd(src, w, frames, nc, save_input=True)
+    zf = z.float()
+    a = zf * sc + sh if bn else zf
+    a = F.leaky_relu(a, 0.2).to(torch.bfloat16)
+    assert torch.equal(a_out, a) or rel(a_out, a) < 1e-2
+    ref = torch.sigmoid(F.conv_transpose2d(a_out.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1))
+    assert float((xh - ref).abs().max()) < 2e-3, float((xh - ref).abs().max())
+    r = ops.conv3x3([src], ops.pack_conv3x3(w, 'convT'), frames, 64, 64, nc, sigmoid_nchw=True, save_input=True)
+    assert float((xh - r[0]).abs().max()) < 2e-3
+    assert torch.equal(a_out, r[2])
