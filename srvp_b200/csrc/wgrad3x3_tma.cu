@@ -45,6 +45,7 @@ struct WgTmaDev {
   int stages_total, splits;
   int num_mblk, num_nblk;    // 64-channel blocks of the activation / dz operand
   int ksteps;                // MMA K steps (16 pixels) per stripe
+  int nb;                    // MMA N = dz channels per CTA: 64, or 16 for a thin dz (the decoder's last layer)
   uint32_t a_block_bytes, d_block_bytes, sub_bytes, stage_bytes, tx_bytes;
   int nstg;
   int nops;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
     // The WHOLE warp runs the loop converged and only the tcgen05 instructions are predicated on one elected lane: inside a
     // `lane == 0` branch the compiler cannot use the uniform datapath and wraps every MMA in an elect / R2UR broadcast loop.
     if (nst > 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(128, p.nb, 1, 1);
       const uint32_t tile0 = smem_u32(tiles) >> 4;
       uint32_t a_lo[kMaxOps], a_hi[kMaxOps], dcol[kMaxOps];
 #pragma unroll
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
       // of this block are 2304 contiguous bytes of dW. The accumulators are transposed through the (now idle) pipeline buffers into
       // [co][ci][tap] and added with 16-byte red.global.add.v4.f32 -- 4 full sectors per warp instruction instead of 32 scattered
       // 4-byte atomics (the scattered version cost more than the whole main loop: profiles/r03c_wgrad_ablate.log).
-      const bool fast = !(p.dbg & 16) && p.flip == 0 && p.stride_cin == 9 && (p.stride_cout % 4) == 0 && (mblk * 64 + 64) <= p.cin_real &&
+      const bool fast = !(p.dbg & 16) && p.nb == 64 && p.flip == 0 && p.stride_cin == 9 && (p.stride_cout % 4) == 0 && (mblk * 64 + 64) <= p.cin_real &&
                         (nblk * 64 + 64) <= p.cout_real && (reinterpret_cast<uintptr_t>(p.dw) % 16) == 0 && (size_t)p.nstg * p.stage_bytes >= 64 * 576 * 4;
       if (fast) {
         float* stg = reinterpret_cast<float*>(tiles);     // [64 co][64 ci][9 taps] fp32 = 147 KB
@@ -224,8 +225,15 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
           const int tap = p.ops[o].tap[tb];
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 32) {
+            if (c0 >= p.nb) break;
             float vals[32];
-            tmem_ld32(acc + (uint32_t)p.ops[o].col + c0, vals);
+            if (p.nb >= 32) {
+              tmem_ld32(acc + (uint32_t)p.ops[o].col + c0, vals);
+            } else {
+              tmem_ld16(acc + (uint32_t)p.ops[o].col + c0, vals);
+#pragma unroll
+              for (int n = 16; n < 32; ++n) vals[n] = 0.f;
+            }
             if (tap >= 0 && ci < p.cin_real) {
               const int te = p.flip ? 8 - tap : tap;
               float* dst = p.dw + (long long)ci * p.stride_cin + te;
@@ -285,7 +293,11 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("SRVP_WGRAD_TMA"); enabled = e ? atoi(e) : 1; }
   if (!enabled || a->map4 != 0) return 0;
-  if (a->act_channels % 64 != 0 || a->dz_channels % 64 != 0 || a->act_channels < 64 || a->dz_channels < 64) return 0;
+  // operands: multiples of 64 channels, or a thin 16-channel tensor (first encoder layer's input, last decoder layer's dz): its TMA
+  // box still asks for 64 channels, the out-of-bound ones arrive as zeros
+  const bool act_ok = a->act_channels == 16 || (a->act_channels >= 64 && a->act_channels % 64 == 0);
+  const bool dz_ok = a->dz_channels == 16 || (a->dz_channels >= 64 && a->dz_channels % 64 == 0);
+  if (!act_ok || !dz_ok) return 0;
   if (a->W + 2 > 160 || a->W < 1 || a->H < 1) return 0;
   if ((reinterpret_cast<uintptr_t>(a->act) + (size_t)a->act_coff * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(a->dz) + (size_t)a->dz_coff * 2) % 16 != 0) return 0;
   WgTmaDev d{};
@@ -313,8 +325,9 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
   if (nstg > kMaxStg) nstg = kMaxStg;
   if (nstg < 2) return 0;
   d.nstg = nstg;
-  d.num_mblk = a->act_channels / 64;
-  d.num_nblk = a->dz_channels / 64;
+  d.num_mblk = (a->act_channels + 63) / 64;
+  d.num_nblk = (a->dz_channels + 63) / 64;
+  d.nb = a->dz_channels >= 64 ? 64 : 16;
   const int sms = num_sms_cached();
   const int pairs = d.num_mblk * d.num_nblk;
   int splits = sms / pairs;

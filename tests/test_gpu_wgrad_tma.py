@@ -158,3 +158,29 @@ def test_decoder_head_kernel_matches_torch(dev, nc, frames, bn):
     r = ops.conv3x3([src], ops.pack_conv3x3(w, 'convT'), frames, 64, 64, nc, sigmoid_nchw=True, save_input=True)
     assert float((xh - r[0]).abs().max()) < 2e-3
     assert torch.equal(a_out, r[2])
+
+
+def test_wgrad_tma_thin_operands(dev):
+    """The HBM-bound ends: first encoder layer (16-channel padded input, 3 real channels) and last decoder layer (transposed convolution,
+    dz padded to 16 channels, 3 real): the TMA boxes ask for 64 channels, the missing ones arrive as out-of-bound zeros."""
+    from srvp_b200 import ops
+    torch.manual_seed(11)
+    frames, H = 5, 64
+    # first layer: nn.Conv2d(3, 64): act = x padded to 16 channels
+    x = torch.rand(frames, 3, H, H, device=dev).to(torch.bfloat16)
+    dz = (torch.randn(frames, 64, H, H, device=dev) * 0.1).to(torch.bfloat16)
+    ref = _reference(x, dz, 'conv', 64, 3)
+    x16 = torch.zeros(frames, H, H, 16, device=dev, dtype=torch.bfloat16)
+    x16[..., :3] = x.permute(0, 2, 3, 1)
+    dw = torch.zeros_like(ref)
+    ops.wgrad3x3(x16, 16, dz.permute(0, 2, 3, 1).contiguous(), 64, frames, H, H, 64, 3, dw, 'conv')
+    assert rel(dw, ref) < 2e-3, rel(dw, ref)
+    # last layer: nn.ConvTranspose2d(64, 3): dz padded to 16 channels
+    a = (torch.randn(frames, 64, H, H, device=dev) * 0.5).to(torch.bfloat16)
+    dz3 = (torch.randn(frames, 3, H, H, device=dev) * 0.1).to(torch.bfloat16)
+    ref = _reference(a, dz3, 'convT', 3, 64)
+    dz16 = torch.zeros(frames, H, H, 16, device=dev, dtype=torch.bfloat16)
+    dz16[..., :3] = dz3.permute(0, 2, 3, 1)
+    dw = torch.zeros_like(ref)
+    ops.wgrad3x3(a.permute(0, 2, 3, 1).contiguous(), 64, dz16, 16, frames, H, H, 3, 64, dw, 'convT')
+    assert rel(dw, ref) < 2e-3, rel(dw, ref)
