@@ -80,9 +80,10 @@ typedef struct {
   /* --- convolution over torch.cat([h, skip], 1) (conv.py:270) split as conv_h(h) + conv_s(skip): the skip features are the same
    * for every time step of a video (srvp.py:222-223), so conv_s runs once per VIDEO (fp32 result, out_raw_f32) and the per-frame
    * launch adds it to its accumulators before rounding / statistics (add_f32, frame f uses row f % add_frames) --- */
-  const float* add_f32;   /* optional (add_frames, H, W, cout) fp32 */
+  const float* add_f32;   /* optional fp32 addend of add_frames frames, laid out [cout/4][add_frames*H*W][4] (channel-group planes: the
+                             epilogue thread owns a pixel, so lanes read consecutive 16-byte pieces of a plane) */
   int32_t add_frames;
-  float* out_raw_f32;     /* optional (frames, H, W, cout) fp32 copy of the raw result; `out` may then be NULL */
+  float* out_raw_f32;     /* optional fp32 copy of the raw result in the same [cout/4][frames*H*W][4] layout; `out` may then be NULL */
 } srvp_conv3x3_args;
 
 /* Number of rows of stats_partial srvp_conv3x3 writes for this geometry / channel count (= its persistent grid size). */

@@ -30,7 +30,7 @@ namespace srvp {
 namespace {
 
 // warps 0-3 epilogue, 4..4+kLoaderWarps-1 activation loaders, then the MMA issuer warp and the weight TMA-bulk issuer warp.
-// Twelve loader warps (sixteen spilled at 80 registers per thread and were slower): the fused BN + LeakyReLU transform of the operand loader is instruction-bound (two loader warps per scheduler
+// Twelve loader warps: the fused BN + LeakyReLU transform of the operand loader is instruction-bound (two loader warps per scheduler
 // could not hide their own dependency stalls; with copies, MMAs and stores all disabled a forward launch still took 85 % of its time,
 // profiles/r03h_thin.log), so the forward convolutions scale with the number of loader warps until the MMAs take over.
 constexpr int kLoaderWarps = 12;
@@ -117,9 +117,8 @@ struct Cfg {
   static constexpr int MIN_WSLOTS = (KCH != 8) ? 2 : (NB >= 256 ? 3 : 4);  // the host adds slots while shared memory allows (ConvDev.wslots)
   static constexpr int MAX_WSLOTS = 8;
   static constexpr int SLOT_BYTES = TPS * KCH * NB * 16;
-  // fp32 columns staged per pass through shared memory (32 for the 64-column variant: its 512-pixel halo tile leaves no room for more)
-  static constexpr int STAGE_COLS = NB <= 64 ? 32 : 64;
-  static constexpr int STAGE_PITCH = STAGE_COLS * 4 + 16;  // bytes per staged row (the 16-byte pad keeps both access patterns conflict-free)
+  static constexpr int STAGE_COLS = NB < 128 ? NB : 128;  // output columns staged per pass through shared memory
+  static constexpr int STAGE_PITCH = STAGE_COLS * 2 + 16;  // bytes per staged output row
   static constexpr int STAGING_BYTES = (EPI == SRVP_EPI_RAW_BF16) ? 128 * STAGE_PITCH : 0;
   static constexpr int ACC_COLS = MBLK * NB;  // per accumulator stage
   // two accumulator stages (epilogue of tile i overlaps the MMAs of tile i+1) when they fit in the 512 TMEM columns, else one
@@ -129,7 +128,7 @@ struct Cfg {
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(9 % TPS == 0, "taps per slot must divide 9");
   static size_t smem_bytes(int P, int wslots) {
-    return (size_t)kHaloStages * KCH * P * 16 + (size_t)wslots * SLOT_BYTES + STAGING_BYTES + 2 * 128 * 4 + 2 * NB * 2 * 4 + 64 * 8 + 16;
+    return (size_t)kHaloStages * KCH * P * 16 + (size_t)wslots * SLOT_BYTES + STAGING_BYTES + 128 * 4 + 2 * NB * 2 * 4 + 64 * 8 + 16;
   }
 };
 
@@ -142,9 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   uint8_t* wslots = halo + (size_t)kHaloStages * KCH * P * 16;
   const int WS = p.wslots;  // weight-ring depth: the ring round trip (MMA commit -> refill from L2 -> MMA) is ~1 us, it must cover it
   uint8_t* staging = wslots + (size_t)WS * C::SLOT_BYTES;
-  int* rowpix = reinterpret_cast<int*>(staging + C::STAGING_BYTES);   // [128] output pixel index of each tile row (-1: pad row)
-  int* auxpix = rowpix + 128;                                         // [128] dense pixel index (fp32 side output) / addend pixel index
-  float* statbuf = reinterpret_cast<float*>(auxpix + 128);  // [2 N blocks][NB][2]: per-CTA running (sum, sumsq)
+  int* rowpix = reinterpret_cast<int*>(staging + C::STAGING_BYTES);
+  float* statbuf = reinterpret_cast<float*>(rowpix + 128);  // [2 N blocks][NB][2]: per-CTA running (sum, sumsq)
   uint64_t* bars = reinterpret_cast<uint64_t*>(statbuf + 2 * NB * 2);
   uint64_t* halo_full = bars;                    // [kHaloStages]
   uint64_t* halo_empty = bars + kHaloStages;     // [kHaloStages]
@@ -376,12 +374,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
       mbar_wait(&acc_full[as], (tcount / C::ACC_STAGES) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
-      // Column-owner pass (see below): LPR lanes share a row, lane column group cg owns 4 columns of every staging pass
-      constexpr int NPASS = (EPI == SRVP_EPI_RAW_BF16) ? NB / C::STAGE_COLS : 1;
-      constexpr int LPR = C::STAGE_COLS / 4, RPI = 32 / LPR;
-      float s1[NPASS * 4], s2[NPASS * 4];
+      constexpr int NBAT = (NB + 31) / 32;  // 32-column batches; lane l accumulates column batch*32 + l over this warp's rows
+      float s1[NBAT], s2[NBAT];
 #pragma unroll
-      for (int i = 0; i < NPASS * 4; ++i) s1[i] = s2[i] = 0.f;
+      for (int i = 0; i < NBAT; ++i) s1[i] = s2[i] = 0.f;
       const bool do_stats = p.stats_partial != nullptr;
 
 #pragma unroll 1
@@ -411,57 +407,80 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             }
           }
         } else {
-          // Every warp stages and stores its own 32 rows: only warp-level synchronisation is needed.
-          //   phase A (row owner: thread = accumulator row): TMEM -> registers -> fp32 staging row in shared memory;
-          //   phase B (column owner: LPR lanes per row, 4 columns each): staged fp32 (+ the per-video addend, read with the SAME coalesced
-          //     pattern: 16 bytes per lane, a whole row per LPR lanes) -> rounded to bf16 -> 8-byte coalesced stores; the per-channel
-          //     (sum, sumsq) of the stored bf16 values accumulate in the lane's registers (it owns the same 4 columns for every row).
-          // The addend used to be read by the row owner (32 scattered 16-byte requests per instruction, +1.06 ms on the 64-channel 64x64
-          // layer, profiles/r03k_fwd_ablate.log) and the statistics needed a third pass over the staged tile.
-          const int dense = (f * p.H + y) * p.W + x;
+          // every warp stages, reduces and stores its own 32 rows: only warp-level synchronisation is needed
           rowpix[tid] = valid ? ((f * p.H + y) * p.out_row_pitch + x * p.out_xstride) : -1;
-          auxpix[tid] = p.add != nullptr ? (((f % (p.add_frames > 0 ? p.add_frames : 1)) * p.H + y) * p.W + x) : dense;
-          float* srow = reinterpret_cast<float*>(staging + (size_t)tid * C::STAGE_PITCH);
-          constexpr int BPP = C::STAGE_COLS / 32;  // 32-column TMEM batches per staging pass
-          const int cg = lane % LPR, rsel = lane / LPR;
+          uint8_t* srow = staging + (size_t)tid * C::STAGE_PITCH;
+          constexpr int BPP = C::STAGE_COLS / 32;  // 32-column batches per staging pass
 #pragma unroll
-          for (int ps = 0; ps < NPASS; ++ps) {
+          for (int ps = 0; ps < NB / C::STAGE_COLS; ++ps) {
 #pragma unroll
             for (int bb = 0; bb < BPP; ++bb) {
+              const int bi = ps * BPP + bb;
               float vals[32];
-              tmem_ld32(acc + mb * NB + (ps * BPP + bb) * 32, vals);
+              tmem_ld32(acc + mb * NB + bi * 32, vals);
+              // The fp32 per-video tensor (written through out_raw_f32 by one launch, added through `add` by another) is laid out as
+              // [cout / 4][frames * H * W][4]: the epilogue thread owns a ROW (pixel), so consecutive lanes = consecutive pixels read /
+              // write consecutive 16-byte pieces of one channel-group plane -- coalesced. In the pixel-major (frames, H, W, cout)
+              // layout every one of these requests touched 32 different 128-byte lines and the addend cost more than the MMAs of the
+              // 64-channel 64x64 layer (+1.06 ms, profiles/r03k_fwd_ablate.log).
+              if (p.add != nullptr && valid) {
+                // per-video term of a convolution split over cat[h, skip]: conv(cat[h, s]) = conv_h(h) + conv_s(s), s constant over time
+                const size_t npix = (size_t)p.add_frames * p.H * p.W;
+                const float4* ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nblk * NB + bi * 32) >> 2) * npix +
+                                   (size_t)(((f % p.add_frames) * p.H + y) * p.W + x);
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(srow + bb * 32 + q * 4) = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t4 = __ldg(ap + (size_t)q * npix);
+                  vals[4 * q] += t4.x; vals[4 * q + 1] += t4.y; vals[4 * q + 2] += t4.z; vals[4 * q + 3] += t4.w;
+                }
+              }
+              if (p.out_raw_f32 != nullptr && valid) {
+                const size_t npix = (size_t)p.F * p.H * p.W;
+                float4* op = reinterpret_cast<float4*>(p.out_raw_f32) + (size_t)((nblk * NB + bi * 32) >> 2) * npix + (size_t)((f * p.H + y) * p.W + x);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) op[(size_t)q * npix] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+              }
+              uint32_t pk[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) pk[q] = valid ? pack_bf16x2(vals[2 * q], vals[2 * q + 1]) : 0u;  // pad rows: zeros (never stored)
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(srow + bb * 64 + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
-            if (mb == C::MBLK - 1 && ps == NPASS - 1) {
+            if (mb == C::MBLK - 1 && ps == NB / C::STAGE_COLS - 1) {
               tc_fence_before();
               mbar_arrive(&acc_empty[as]);
             }
             __syncwarp();
-            const int col0 = nblk * NB + ps * C::STAGE_COLS + cg * 4;
-            if (col0 < p.cout) {
-#pragma unroll 4
-              for (int it = 0; it < 32 / RPI; ++it) {
-                const int r = warp * 32 + it * RPI + rsel;
-                const int pix = rowpix[r];
-                if (pix >= 0) {
-                  float4 v = *reinterpret_cast<const float4*>(staging + (size_t)r * C::STAGE_PITCH + cg * 16);
-                  if (p.add != nullptr) {
-                    // per-video term of a convolution split over cat[h, skip]: conv(cat[h, s]) = conv_h(h) + conv_s(s), s constant over time
-                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.add + (size_t)auxpix[r] * p.cout + col0));
-                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
-                  }
-                  if (p.out_raw_f32 != nullptr) *reinterpret_cast<float4*>(p.out_raw_f32 + (size_t)auxpix[r] * p.cout + col0) = v;
-                  const uint32_t lo = pack_bf16x2(v.x, v.y), hi = pack_bf16x2(v.z, v.w);
-                  if (p.out != nullptr && !(p.dbg & 4)) *reinterpret_cast<uint2*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + col0) = make_uint2(lo, hi);
-                  if (do_stats) {
-                    const float2 u0 = unpack_bf16x2(lo), u1 = unpack_bf16x2(hi);
-                    s1[ps * 4 + 0] += u0.x; s1[ps * 4 + 1] += u0.y; s1[ps * 4 + 2] += u1.x; s1[ps * 4 + 3] += u1.y;
-                    s2[ps * 4 + 0] = fmaf(u0.x, u0.x, s2[ps * 4 + 0]); s2[ps * 4 + 1] = fmaf(u0.y, u0.y, s2[ps * 4 + 1]);
-                    s2[ps * 4 + 2] = fmaf(u1.x, u1.x, s2[ps * 4 + 2]); s2[ps * 4 + 3] = fmaf(u1.y, u1.y, s2[ps * 4 + 3]);
-                  }
+            if (do_stats) {
+              // per-channel (sum, sumsq) of the stored bf16 values over this warp's 32 rows: lane l owns the column pairs l, l+32, ...
+              const uint8_t* wrows = staging + (size_t)(warp * 32) * C::STAGE_PITCH;
+#pragma unroll
+              for (int cp = 0; cp < C::STAGE_COLS / 64; ++cp) {
+                float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  const float2 v2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(wrows + (size_t)r * C::STAGE_PITCH + (cp * 32 + lane) * 4));
+                  a0 += v2.x; a1 += v2.y;
+                  q0 = fmaf(v2.x, v2.x, q0); q1 = fmaf(v2.y, v2.y, q1);
                 }
+                const int slot = (ps * (C::STAGE_COLS / 64) + cp) * 2;
+                s1[slot] += a0; s1[slot + 1] += a1;
+                s2[slot] += q0; s2[slot + 1] += q1;
+              }
+            }
+            // coalesced store of the valid rows
+            constexpr int LPR = C::STAGE_COLS / 8;  // lanes per row (16 B each)
+            constexpr int RPI = 32 / LPR;           // rows per warp instruction
+            const int lrow = lane / LPR, lcol = lane % LPR;
+            const int cbase = nblk * NB + ps * C::STAGE_COLS + lcol * 8;
+#pragma unroll 4
+            for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
+              const int r = r0 + lrow;
+              const int pix = rowpix[r];
+              if (pix >= 0 && cbase < p.cout && p.out != nullptr && !(p.dbg & 4)) {
+                const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
+                *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
               }
             }
             __syncwarp();
@@ -470,25 +489,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
       }
       if constexpr (EPI == SRVP_EPI_RAW_BF16) {
         if (do_stats) {
-          // combine the RPI row lanes that own the same columns, then add this tile's column sums to the per-CTA accumulators, one
-          // warp after the other (fixed order: deterministic)
-#pragma unroll
-          for (int i = 0; i < NPASS * 4; ++i) {
-#pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) {
-              s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-              s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-            }
-          }
+          // add this tile's column sums to the per-CTA accumulators, one warp after the other (fixed order: deterministic)
           float* wacc = statbuf + ((nblk & 1) * NB) * 2;
 #pragma unroll 1
           for (int w = 0; w < 4; ++w) {
-            if (warp == w && lane < LPR) {
+            if (warp == w) {
 #pragma unroll
-              for (int i = 0; i < NPASS * 4; ++i) {
-                const int col = (i >> 2) * C::STAGE_COLS + lane * 4 + (i & 3);
-                wacc[col * 2 + 0] += s1[i];
-                wacc[col * 2 + 1] += s2[i];
+              for (int sl = 0; sl < NBAT; ++sl) {
+                const int col = (sl >> 1) * 64 + lane * 2 + (sl & 1);   // pair set, lane's pair, element of the pair
+                wacc[col * 2 + 0] += s1[sl];
+                wacc[col * 2 + 1] += s2[sl];
               }
             }
             named_bar_sync(1, 128);

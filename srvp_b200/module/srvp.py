@@ -93,6 +93,12 @@ class StochasticLatentResidualVideoPredictor(nn.Module):
         hx, handle = self._encode_fused(x)
         if handle is None:
             return hx, None
+        if self.training and torch.is_grad_enabled() and not getattr(self, '_warned_skip_grad', False):
+            import warnings
+            warnings.warn('srvp_b200: encode() returns the skip connections as materialised tensors outside autograd: gradients reach the '
+                          'encoder through hx only. Training code should call forward() (as the reference train.py does), which routes the '
+                          'skip gradients back to the encoder.')
+            self._warned_skip_grad = True
         from .. import ops
         skips = []
         for (z, st, C, res) in handle.levels:

@@ -246,11 +246,13 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
         a.out_f32_nchw = ptr(out)
     else:
         a.epilogue = _lib.EPI_RAW_BF16
-        if add is not None:        # fp32 (add_frames, H, W, cout): per-video term added to the accumulators (frame f -> f % add_frames)
-            assert add.dtype == torch.float32 and tuple(add.shape[1:]) == (H, W, cout) and frames % add.shape[0] == 0
-            a.add_f32, a.add_frames = ptr(add), add.shape[0]
-        if out_f32:                # raw result kept in fp32 only (the per-video term itself)
-            out = torch.empty(frames, H, W, cout, dtype=torch.float32, device=dev)
+        if add is not None:        # fp32 (cout/4, add_frames*H*W, 4) channel-group planes: per-video term added to the accumulators (frame f -> f % add_frames)
+            assert add.dtype == torch.float32 and add.shape[0] == cout // 4 and add.shape[2] == 4 and add.shape[1] % (H * W) == 0
+            add_frames = add.shape[1] // (H * W)
+            assert frames % add_frames == 0
+            a.add_f32, a.add_frames = ptr(add), add_frames
+        if out_f32:                # raw result kept in fp32 only (the per-video term itself), as channel-group planes [cout/4][frames*H*W][4]
+            out = torch.empty(cout // 4, frames * H * W, 4, dtype=torch.float32, device=dev)
             a.out_raw_f32 = ptr(out)
             a.out_cpitch = cout
         else:

@@ -110,11 +110,10 @@ def allreduce_bn_partial(partial, count):
 
     No host synchronisation: every rank holds the same number of positions (the reference asserts batch_size % n_gpu == 0,
     train.py:218), so the global count is count * world_size and only the 2C sums travel (one latency-bound all-reduce)."""
-    tot = partial.sum(0, keepdim=True)
-    if world() == 1:
-        return tot, float(count)
-    dist.all_reduce(tot)
-    return tot, float(count) * world()
+    tot = partial.sum(0, keepdim=True, dtype=torch.float64)     # rows and ranks are added in fp64, like the single-GPU finalisation
+    if world() > 1:
+        dist.all_reduce(tot)
+    return tot.float(), float(count) * world()
 
 
 class PeerBN:

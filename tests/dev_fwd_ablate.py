@@ -28,7 +28,7 @@ for (name, C, H, mode) in [('64@64 DIRECT', 64, 64, 0), ('64@64 UP2', 64, 64, 2)
     sc, sh = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
     w = torch.randn(cout, C, 3, 3, device=dev) * 0.05
     wp = ops.pack_conv3x3(w, 'conv')
-    add = torch.randn(B, H, H, cout, device=dev)
+    add = torch.randn(cout // 4, B * H * H, 4, device=dev)
     plain = ops.Src(z, C, None, None, None, 0, mode, False)
     fused = ops.Src(z, C, sc, sh, None, 0, mode, True)
     res = {}

@@ -184,3 +184,26 @@ def test_wgrad_tma_thin_operands(dev):
     dw = torch.zeros_like(ref)
     ops.wgrad3x3(a.permute(0, 2, 3, 1).contiguous(), 64, dz16, 16, frames, H, H, 3, 64, dw, 'convT')
     assert rel(dw, ref) < 2e-3, rel(dw, ref)
+
+
+@pytest.mark.parametrize('C,H', [(64, 16), (256, 8)])
+def test_conv3x3_per_video_addend_split(dev, C, H):
+    """conv(cat[h, s]) = conv_h(h) + conv_s(s) with s constant over time (engine._decoder_fwd): the per-video term goes through the fp32
+    side output of one launch (channel-group planes) into the `add` input of the other; result vs F.conv2d over the concatenation."""
+    from srvp_b200 import ops
+    torch.manual_seed(C)
+    nt, B = 3, 4
+    Fr = nt * B
+    h = (torch.randn(Fr, H, H, C, device=dev) * 0.5).to(torch.bfloat16)
+    sk = (torch.randn(B, H, H, C, device=dev) * 0.5).to(torch.bfloat16)
+    w = torch.randn(C, 2 * C, 3, 3, device=dev) * 0.03
+    wb = w.to(torch.bfloat16).float()
+    cat = torch.cat([h.float(), sk.float().repeat(nt, 1, 1, 1)], 3).permute(0, 3, 1, 2)
+    ref = F.conv2d(cat, wb, padding=1).permute(0, 2, 3, 1)
+    rs = ops.conv3x3([ops.Src(sk, C)], ops.pack_conv3x3(w, 'conv', cin_range=(C, C)), B, H, H, C, out_f32=True)
+    assert tuple(rs[0].shape) == (C // 4, B * H * H, 4)
+    r = ops.conv3x3([ops.Src(h, C)], ops.pack_conv3x3(w, 'conv', cin_range=(0, C)), Fr, H, H, C, stats=True, add=rs[0])
+    assert rel(r[0].float(), ref) < 1.5e-2
+    tot = r[1].sum(0)                                    # (C, 2): sum, sumsq of the stored bf16 values
+    zs = r[0].float().view(-1, C)
+    assert rel(tot[:, 0], zs.sum(0)) < 1e-3 and rel(tot[:, 1], (zs * zs).sum(0)) < 1e-3
