@@ -575,10 +575,12 @@ def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=F
         planes = torch.empty(det_split, M, N, dtype=torch.float32, device=c.device)
         _gemm_call(a, b, planes[0], None, False, act, False, det_split, M * N)
         check(lib().srvp_sum_slices_f32(ptr(planes), ptr(c), c_int(det_split), c_i64(M * N), stream_ptr()), 'sum_slices')
-        _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N)
+        _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N,
+                 desc=f'M={M} N={N} K={K} det_split={det_split} a{tuple(a.stride())} b{tuple(b.stride())} {a.dtype} {b.dtype}')
         return c
     _gemm_call(a, b, c, bias, bias_on_m, act, accumulate, split_k, 0)
-    _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N)
+    _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N,
+             desc=f'M={M} N={N} K={K} acc={int(accumulate)} a{tuple(a.stride())} b{tuple(b.stride())} {a.dtype} {b.dtype}')
     return c
 
 
