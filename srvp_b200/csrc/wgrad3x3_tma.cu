@@ -321,7 +321,13 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
   d.sub_bytes = d.a_block_bytes + d.d_block_bytes;
   d.stage_bytes = d.sub_bytes * d.NSUB;
   d.tx_bytes = (uint32_t)d.NSUB * (uint32_t)(Ka + Kd) * 128;
-  int nstg = (int)((227 * 1024 - 2048) / d.stage_bytes);
+  // Shared-memory budget of the operand ring. The default leaves ~38 KB of the SM free so that two blocks of the HBM-bound batch-norm
+  // backward kernels (18 KB static each) can be resident NEXT to this tensor-bound kernel when the weight gradients run on their own
+  // stream (srvp_b200/ops.py: wgrad stream); SRVP_WGRAD_SMEM_KB overrides (227 = everything).
+  static int smem_kb = -1;
+  if (smem_kb < 0) { const char* e = getenv("SRVP_WGRAD_SMEM_KB"); smem_kb = e ? atoi(e) : 188; if (smem_kb > 227) smem_kb = 227; if (smem_kb < 64) smem_kb = 64; }
+  int nstg = (int)(((size_t)smem_kb * 1024 - 2048) / d.stage_bytes);
+  if (nstg < 3) nstg = (int)((227 * 1024 - 2048) / d.stage_bytes) < 3 ? (int)((227 * 1024 - 2048) / d.stage_bytes) : 3;   // never below 3 stages if they fit at all
   if (nstg > kMaxStg) nstg = kMaxStg;
   if (nstg < 2) return 0;
   d.nstg = nstg;

@@ -192,6 +192,7 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
     ops.gemm(dz_last, c.wl.view(enc.nh, 16 * C).t(), da.view(F_, 16 * C))
     if plan == 'dcgan':
         _dcgan_encoder_convs_bwd(enc, c, da, grads, skip_handle)
+        ops.join_wgrads()
         return _returned(grads, direct)
     da_mode = SRC_POOL2
     for li in range(len(plan) - 1, -1, -1):
@@ -204,11 +205,12 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[3 * li + 1], grads[3 * li + 2], da, da_mode, F_, blk.res, blk.res,
                         blk.cout, sync=ops.is_sync_bn(blk.bn), **kw)
         cin_real = blk.cin
-        ops.wgrad3x3(c.srcs[li], c.srcs[li].shape[-1], dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_real, grads[3 * li], 'conv')
+        ops.wgrad3x3(c.srcs[li], c.srcs[li].shape[-1], dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_real, grads[3 * li], 'conv', defer=True)
         if li > 0:
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, blk.cin)
             da_mode = blk.in_mode  # POOL2: the producer is at twice this resolution
+    ops.join_wgrads()      # weight gradients run on their own stream (ops.py): final before autograd / the optimizer sees them
     return _returned(grads, direct)
 
 
@@ -360,7 +362,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     final = dec.conv[3][1]
     nc = final.out_channels
     dz = ops.sigmoid_bwd(d_xhat.contiguous(), c.x_hat)  # (F,64,64,16)
-    ops.wgrad3x3(c.final_a, final.in_channels, dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT')
+    ops.wgrad3x3(c.final_a, final.in_channels, dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT', defer=True)
     wp = ops.pack_conv3x3(final.weight, 'convT_dgrad')
     da, _ = ops.conv3x3([Src(dz, 16)], wp, F_, 64, 64, final.in_channels, cin_real=nc)
     da_mode, da_coff = SRC_DIRECT, 0
@@ -376,10 +378,10 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
             ch = c.srcs[li].shape[-1]
             cin_tot = ch + cs
             ops.wgrad3x3(c.srcs[li], ch, dz, blk.cout, F_, blk.res, blk.res, blk.cout, ch, grads[gi], 'conv', strides=(cin_tot * 9, 9),
-                         alg_scale=cin_tot / ch)
+                         alg_scale=cin_tot / ch, defer=True)
             dzs = ops.sum_over_time(dz, F_ // nvid)
             ops.wgrad3x3(a_s, cs, dzs, blk.cout, nvid, blk.res, blk.res, blk.cout, cs, grads[gi], 'conv', strides=(cin_tot * 9, 9), dw_offset=ch * 9,
-                         alg_scale=0.0)
+                         alg_scale=0.0, defer=True)
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad', cin_range=(0, ch))
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, ch, alg_scale=cin_tot / ch)
             wp_s = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad', cin_range=(ch, cs))
@@ -387,7 +389,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
             skip_grads[blk.skip_level] = (d_skip, 0)       # already summed over time: the encoder sees nt = 1
         else:
             cin_tot = c.srcs[li].shape[-1]
-            ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv')
+            ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv', defer=True)
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, cin_tot)
             if blk.skip_level is not None:
@@ -409,6 +411,14 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads, direct):
     dwp = torch.zeros(nin, 16, C0, dtype=torch.float32, device=dev)
     ops.gemm(c.dec_inp.t(), dz0.view(F_, 16 * C0).t(), dwp.view(nin, 16 * C0), accumulate=True)
     ops.transpose_last2(dwp, out=grads[0])
+    # The decoder's weight gradients may keep running under the latent / inference-network backward (few-CTA, latency-bound kernels)
+    # when every gradient lives in the GradBucket (consumed only after allreduce_mean() / Adam.step(), which join) and no early
+    # all-reduce of the decoder segment is about to read them; otherwise they must be final here.
+    from . import parallel
+    if all(direct) and ops.DEFER_JOIN and parallel.world() == 1:
+        ops.flush_wgrads()
+    else:
+        ops.join_wgrads()
     return d_inp, _returned(grads, direct)
 
 
@@ -538,7 +548,7 @@ def _dcgan_encoder_convs_bwd(enc, c, da, grads, skip_handle):
                         sync=ops.is_sync_bn(bn_i), **skip_kw(i))
         # dW[co, ci, ky, kx]: the 3x3 weight-gradient kernel over (S2D input saved by the forward loader, dz)
         ops.wgrad3x3(c.srcs[i], 4 * cin, dz, cout, F_, res, res, cout, 4 * cin, grads[gi], 'conv', map4=W4_DOWN, phase_channels=cin,
-                     strides=(cin * 16, 16))
+                     strides=(cin * 16, 16), defer=True)
         # data gradient = the transposed convolution: n = ci (stride 16), k = co (stride cin*16)
         da = torch.empty(F_, 2 * res, 2 * res, cin, dtype=torch.bfloat16, device=dz.device)
         _up_conv([Src(dz, cout)], conv_i.weight, 16, cin * 16, F_, res, res, cin, cout, stats=False, a_out=None, out=da)
@@ -546,7 +556,7 @@ def _dcgan_encoder_convs_bwd(enc, c, da, grads, skip_handle):
     dz0 = ops.lrelu_bwd(c.z[0], da, F_, 32, 32, conv0.out_channels, **skip_kw(0))
     nc = enc.nc
     ops.wgrad3x3(c.xs, 16, dz0, conv0.out_channels, F_, 32, 32, conv0.out_channels, 4 * nc, grads[0], 'conv', map4=W4_DOWN, phase_channels=nc,
-                 strides=(nc * 16, 16))
+                 strides=(nc * 16, 16), defer=True)
 
 
 def _dcgan_decoder_convs_fwd(dec, c, prev, skip_levels, frame_map, training, want_stats_update):
@@ -596,7 +606,7 @@ def _dcgan_decoder_convs_bwd(dec, c, d_xhat, grads, skip_handle):
     dz16 = ops.sigmoid_bwd_s2d(d_xhat.contiguous(), c.x_hat)            # (F,32,32,16): channel (py,px,c)
     # weight (cin, nc, 4, 4): dz-side channel co has stride 16, act-side channel ci stride nc*16
     ops.wgrad3x3(c.final_a, cin_f, dz16, 16, F_, 32, 32, 4 * nc, cin_f, grads[-1], 'convT', map4=W4_UP_ALL, phase_channels=nc,
-                 strides=(16, nc * 16))
+                 strides=(16, nc * 16), defer=True)
     # data gradient: the forward stride-2 convolution of dz with the same weight: n = ci (stride nc*16), k = (py,px,co) (stride 16);
     # the thin-K kernel variant has a 64-channel N block: one launch per 64 input channels
     da = torch.empty(F_, 32, 32, cin_f, dtype=torch.bfloat16, device=dev)
@@ -615,7 +625,7 @@ def _dcgan_decoder_convs_bwd(dec, c, d_xhat, grads, skip_handle):
         res //= 2
         # dW[ci, co, ky, kx] = sum a[p, ci] * S2D(dz)[p + tap, (py,px,co)]: "act" = S2D(dz) (phased), "dz" = the saved input a
         ops.wgrad3x3(dzs, 4 * cout, c.srcs[i], cin_tot, F_, res, res, cin_tot, 4 * cout, grads[gi], 'conv', map4=W4_DOWN, phase_channels=cout,
-                     strides=(cout * 16, 16))
+                     strides=(cout * 16, 16), defer=True)
         # data gradient: stride-2 convolution of dz: n = ci (stride cout*16), k = (py,px,co) (stride 16)
         wp = ops.pack_conv4x4s2(convT.weight, W4_DOWN, cin_tot, cout, cout * 16, 16)
         da, _ = ops.conv3x3([Src(dzs, 4 * cout)], wp, F_, res, res, cin_tot, tap_masks=_down_masks(cout, 4 * cout), taps=4)

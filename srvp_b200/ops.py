@@ -1,5 +1,6 @@
 """Tensor-level wrappers over the C ABI (include/srvp_b200.h). No arithmetic happens in Python."""
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -13,6 +14,7 @@ from ._lib import c_int, c_i64, check, lib, ptr, stream_ptr
 # bench.py sets PROFILE = {} for a few extra steps: every wrapper below then brackets its launches with CUDA events on the
 # current stream and records (events, algorithmic flops, algorithmic bytes); summarize_profile() reduces them after a sync.
 PROFILE = None
+TIMELINE = None    # development (tools/step_timeline.py): [(name, stage, stream, start event, end event)] with the side stream left enabled
 PROFILE_TAG = ''   # set by the engine around encoder / decoder forward / backward: per-stage roofline figures in bench.py
 
 
@@ -20,7 +22,14 @@ def profiled(name):
     def deco(fn):
         def wrapper(*args, **kwargs):
             if PROFILE is None:
-                return fn(*args, **kwargs)
+                if TIMELINE is None:
+                    return fn(*args, **kwargs)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*args, **kwargs)
+                e1.record()
+                TIMELINE.append((name, PROFILE_TAG, 'main', e0, e1))
+                return out
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _WORK.append([0.0, 0.0, 0.0, None, ''])
@@ -181,12 +190,74 @@ def pack_conv4x4s2(weight, kind, chan_n, chan_k, stride_n, stride_k, py=0, px=0,
     return out
 
 
+# ------------------------------------------------------------------------------------------------ weight-gradient stream
+# The weight gradients are off the critical path of the backward pass: layer L's dW needs only (a_L, dz_L) and nothing downstream
+# needs dW before the optimizer. They are tensor-bound and leave HBM mostly idle, while the batch-norm backward of the NEXT layer
+# (reduce + apply over da / z, on the critical path) is purely HBM-bound and leaves the tensor cores idle. With SRVP_WGRAD_STREAM=1
+# (default) wgrad3x3() therefore only records its launch; the launch is issued on a second CUDA stream right after the next
+# data-gradient convolution has been enqueued on the main stream (so that the critical-path kernel gets the SMs first), and the
+# blocks of the following batch-norm backward kernels become resident next to the weight-gradient CTAs (csrc/wgrad3x3_tma.cu keeps
+# ~38 KB of shared memory free for them). join_wgrads() makes the main stream wait for everything issued so far; the engine calls it
+# before gradients are handed to autograd / the all-reduce, GradBucket.allreduce_mean() and optim.Adam.step() call it as well.
+# Per-launch profiling (PROFILE is not None) runs everything on the main stream so that the CUDA-event brackets stay meaningful.
+WGRAD_STREAM = int(os.environ.get('SRVP_WGRAD_STREAM', '1'))
+_SIDE_STREAMS = {}
+_DEFERRED = []        # [(args struct, tensors kept alive)]
+_SIDE_BUSY = [False]
+DEFER_JOIN = False    # set by parallel.GradBucket: gradients are only consumed after allreduce_mean() / Adam.step()
+
+
+def _side_stream():
+    dev = torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def flush_wgrads():
+    """Issue the recorded weight-gradient launches on the side stream, behind everything enqueued on the current stream so far."""
+    if not _DEFERRED:
+        return
+    side = _side_stream()
+    sp = _lib.c_ptr(side.cuda_stream)
+    # The side stream waits for everything enqueued on the main stream so far, INCLUDING the data-gradient convolution that follows the
+    # recorded weight gradients in program order: the two cannot share an SM (shared memory), and a weight gradient that becomes
+    # runnable first takes every SM and delays the critical path by its whole duration (profiles/r03q_timeline.log). Released after the
+    # data gradient, it runs next to the batch-norm backward kernels of the following layer instead.
+    ev = torch.cuda.Event()
+    ev.record()
+    side.wait_event(ev)
+    for a, keep in _DEFERRED:
+        if TIMELINE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+        check(lib().srvp_wgrad3x3(ctypes.byref(a), sp), 'wgrad3x3')
+        if TIMELINE is not None:
+            e1.record(side)
+            TIMELINE.append(('wgrad3x3', f'{a.frames}x{a.H} act{a.act_channels} dz{a.dz_channels}', 'side', e0, e1))
+        for t in keep:
+            t.record_stream(side)      # the caching allocator must not hand these buffers out again before the side stream is done
+    _DEFERRED.clear()
+    _SIDE_BUSY[0] = True
+
+
+def join_wgrads():
+    """The current stream waits for every weight-gradient launch recorded so far."""
+    flush_wgrads()
+    if _SIDE_BUSY[0]:
+        torch.cuda.current_stream().wait_stream(_side_stream())
+        _SIDE_BUSY[0] = False
+
+
 @profiled('wgrad3x3')
 def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0, map4=0, phase_channels=0,
-             strides=None, dw_offset=0, alg_scale=1.0):
+             strides=None, dw_offset=0, alg_scale=1.0, defer=False):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
 
-    act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...)."""
+    act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...).
+    defer=True (the engine's backward): the launch is only recorded and issued on the weight-gradient stream by flush_wgrads();
+    the caller must join_wgrads() before dw is read."""
     a = _lib.Wgrad3x3Args()
     assert act.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and dw.dtype == torch.float32
     a.act = ptr(act)
@@ -204,7 +275,10 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
     else:
         a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
     a.map4, a.phase_channels = map4, phase_channels
-    check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
+    if defer and WGRAD_STREAM and PROFILE is None and not torch.cuda.is_current_stream_capturing():
+        _DEFERRED.append((a, (act, dz, dw)))
+    else:
+        check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
     fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
     # thin operands (first encoder / last decoder layer): HBM-bound, also listed by themselves (bench.py hbm_kernels)
     sub = f'hbm:wgrad_thin[{PROFILE_TAG}]' if min(dz_channels, act_channels) <= 16 else None
@@ -481,6 +555,7 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
            inv_map=None, lrelu=True, sync=False, g_s2d=False):
     """Full BN(train)+LeakyReLU(+pool/upsample) backward. Returns dz (bf16, (frames,H,W,C), or its space-to-depth image
     (frames,H/2,W/2,4C) with g_s2d); accumulates dgamma/dbeta."""
+    flush_wgrads()      # the data-gradient convolution of the layer above is enqueued: its weight gradient may follow on the side stream
     dev = z.device
     g = torch.empty((frames, H // 2, W // 2, 4 * C) if g_s2d else (frames, H, W, C), dtype=torch.bfloat16, device=dev)
     rows = lib().srvp_bn_bwd_reduce_rows(c_int(frames), c_int(H), c_int(W), c_int(C), c_int(da_mode))
@@ -515,6 +590,7 @@ _IDENT = {}
 def lrelu_bwd(z, da, frames, H, W, C, *, skip=None, skip_coff=0, nt=0, B=0, inv_map=None):
     """Backward of a bare LeakyReLU (no batch-norm: first DCGAN64 encoder block, module/conv.py:174): dz = lrelu'(z) * (da + skip
     gradient). Runs the apply pass of the BN backward kernel with an identity affine."""
+    flush_wgrads()      # the data-gradient convolution of the layer above is enqueued: its weight gradient may follow on the side stream
     dev = z.device
     key = (dev, C)
     if key not in _IDENT:

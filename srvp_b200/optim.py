@@ -55,6 +55,8 @@ class Adam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from . import ops
+        ops.join_wgrads()      # weight gradients still in flight on their own stream (ops.py) must be final
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group['params'] if p.grad is not None]
             if not params:

@@ -63,6 +63,8 @@ class GradBucket:
         self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
         self._early_work = None
         self.attach()
+        from . import ops
+        ops.DEFER_JOIN = True     # gradients are consumed through allreduce_mean() / optim.Adam.step(), which join the weight-gradient stream
 
     def attach(self):
         for p, v in zip(self.params, self.views):
@@ -90,6 +92,8 @@ class GradBucket:
             self._early_work = self._reduce(self.flat[:self.n_early], async_op=True) or True
 
     def allreduce_mean(self):
+        from . import ops
+        ops.join_wgrads()         # weight gradients still in flight on their own stream (ops.py) are part of the bucket
         if world() == 1:
             return
         if self._early_work is not None:

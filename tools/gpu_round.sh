@@ -16,7 +16,7 @@ for c in d30 e22 d00; do
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3x3_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_conv3x3_$c \
     python tests/dev_prof_conv.py $c > gpurun_out/${tag}_ncu_conv_$c.log 2>&1; echo "ncu conv $c rc=$?"
 done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad3x3_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_wgrad3x3 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad3x3 -s 2 -c 1 -f -o gpurun_out/${tag}_wgrad3x3 \
     python tests/dev_prof_wgrad.py > gpurun_out/${tag}_ncu_wgrad.log 2>&1; echo "ncu wgrad rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:bn_bwd -s 4 -c 4 -f -o gpurun_out/${tag}_bn_bwd \
     python tests/dev_bn_prof.py > gpurun_out/${tag}_ncu_bnbwd.log 2>&1; echo "ncu bn_bwd rc=$?"
