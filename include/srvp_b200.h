@@ -137,6 +137,9 @@ typedef struct {
    * SRVP_W4_UP_ALL: the `dz` channels are. dw is then a (.,.,4,4) weight: index = co*stride_cout + ci*stride_cin + ky*4+kx with
    * co/ci the per-phase channel (< phase_channels on the phased side); (phase, tap) pairs without a 4x4 tap are dropped. */
   int32_t map4, phase_channels;
+  /* 0 = one CTA per SM; > 0 = at most this many CTAs, so that a launch issued on a second stream leaves SMs free for the
+   * latency-bound kernels of the critical path it runs next to (srvp_b200/ops.py: weight-gradient stream). */
+  int32_t max_ctas;
 } srvp_wgrad3x3_args;
 int srvp_wgrad3x3(const srvp_wgrad3x3_args* args, void* stream);
 

@@ -36,7 +36,7 @@ class Conv3x3Args(ctypes.Structure):
 class Wgrad3x3Args(ctypes.Structure):
     _fields_ = [('act', c_ptr), ('act_channels', c_int), ('act_cpitch', c_int), ('act_coff', c_int), ('dz', c_ptr),
                 ('dz_channels', c_int), ('dz_cpitch', c_int), ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
-                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int), ('map4', c_int), ('phase_channels', c_int)]
+                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int), ('map4', c_int), ('phase_channels', c_int), ('max_ctas', c_int)]
 
 
 class BnBwdArgs(ctypes.Structure):

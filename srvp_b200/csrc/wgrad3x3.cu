@@ -327,7 +327,8 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   d.tap_groups = NBc == 64 ? 2 : 1;
   d.num_mblk = (m_ch + 127) / 128;
   d.num_nblk = n_ch / NBc;
-  const int sms = num_sms_cached();
+  int sms = num_sms_cached();
+  if (a->max_ctas > 0 && a->max_ctas < sms) sms = a->max_ctas;
   const int pairs = d.num_mblk * d.num_nblk * d.tap_groups;
   static int waves = 0;            // CTAs per SM over the launch (development override: SRVP_WGRAD_WAVES)
   if (waves == 0) { const char* e = getenv("SRVP_WGRAD_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1) waves = 1; }

@@ -334,7 +334,8 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
   d.num_mblk = (a->act_channels + 63) / 64;
   d.num_nblk = (a->dz_channels + 63) / 64;
   d.nb = a->dz_channels >= 64 ? 64 : 16;
-  const int sms = num_sms_cached();
+  int sms = num_sms_cached();
+  if (a->max_ctas > 0 && a->max_ctas < sms) sms = a->max_ctas;
   const int pairs = d.num_mblk * d.num_nblk;
   int splits = sms / pairs;
   if (splits < 1) splits = 1;

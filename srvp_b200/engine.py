@@ -265,6 +265,9 @@ class _DecCtx:
     pass
 
 
+HOLD_RES = int(__import__('os').environ.get('SRVP_WGRAD_HOLD_RES', '16'))   # decoder layers at or below this resolution: weight gradients held back
+
+
 def _skip_src(level, frame_map):
     if isinstance(level, tuple):
         z, st, C, res = level
@@ -370,6 +373,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     for li in range(len(plan) - 1, -1, -1):
         blk = plan[li]
         gi = 3 + 3 * li
+        hold = blk.res <= HOLD_RES     # see ops.wgrad3x3(hold=True)
         dz = ops.bn_bwd(c.z[li], c.st[li], blk.bn.weight, grads[gi + 1], grads[gi + 2], da, da_mode, F_, blk.res, blk.res, blk.cout,
                         da_coff=da_coff, sync=ops.is_sync_bn(blk.bn))
         if li in c.split:
@@ -378,10 +382,10 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
             ch = c.srcs[li].shape[-1]
             cin_tot = ch + cs
             ops.wgrad3x3(c.srcs[li], ch, dz, blk.cout, F_, blk.res, blk.res, blk.cout, ch, grads[gi], 'conv', strides=(cin_tot * 9, 9),
-                         alg_scale=cin_tot / ch, defer=True)
+                         alg_scale=cin_tot / ch, defer=True, hold=hold)
             dzs = ops.sum_over_time(dz, F_ // nvid)
             ops.wgrad3x3(a_s, cs, dzs, blk.cout, nvid, blk.res, blk.res, blk.cout, cs, grads[gi], 'conv', strides=(cin_tot * 9, 9), dw_offset=ch * 9,
-                         alg_scale=0.0, defer=True)
+                         alg_scale=0.0, defer=True, hold=hold)
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad', cin_range=(0, ch))
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, ch, alg_scale=cin_tot / ch)
             wp_s = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad', cin_range=(ch, cs))
@@ -389,7 +393,7 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
             skip_grads[blk.skip_level] = (d_skip, 0)       # already summed over time: the encoder sees nt = 1
         else:
             cin_tot = c.srcs[li].shape[-1]
-            ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv', defer=True)
+            ops.wgrad3x3(c.srcs[li], cin_tot, dz, blk.cout, F_, blk.res, blk.res, blk.cout, cin_tot, grads[gi], 'conv', defer=True, hold=hold)
             wp = ops.pack_conv3x3(blk.conv.weight, 'conv_dgrad')
             da, _ = ops.conv3x3([Src(dz, blk.cout)], wp, F_, blk.res, blk.res, cin_tot)
             if blk.skip_level is not None:
@@ -416,7 +420,7 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads, direct):
     # all-reduce of the decoder segment is about to read them; otherwise they must be final here.
     from . import parallel
     if all(direct) and ops.DEFER_JOIN and parallel.world() == 1:
-        ops.flush_wgrads()
+        ops.flush_wgrads(held=True)
     else:
         ops.join_wgrads()
     return d_inp, _returned(grads, direct)

@@ -203,6 +203,9 @@ def pack_conv4x4s2(weight, kind, chan_n, chan_k, stride_n, stride_k, py=0, px=0,
 WGRAD_STREAM = int(os.environ.get('SRVP_WGRAD_STREAM', '1'))
 _SIDE_STREAMS = {}
 _DEFERRED = []        # [(args struct, tensors kept alive)]
+_HELD = []            # same, for launches that wait for flush_wgrads(held=True) (see wgrad3x3(hold=True))
+HELD_MAX_CTAS = int(os.environ.get('SRVP_WGRAD_HELD_CTAS', '128'))
+_INFLIGHT = []
 _SIDE_BUSY = [False]
 DEFER_JOIN = False    # set by parallel.GradBucket: gradients are only consumed after allreduce_mean() / Adam.step()
 
@@ -215,8 +218,14 @@ def _side_stream():
     return s
 
 
-def flush_wgrads():
-    """Issue the recorded weight-gradient launches on the side stream, behind everything enqueued on the current stream so far."""
+def flush_wgrads(held=False):
+    """Issue the recorded weight-gradient launches on the side stream, behind everything enqueued on the current stream so far.
+    held=True also issues the launches recorded with hold=True, each limited to HELD_MAX_CTAS CTAs."""
+    if held and _HELD:
+        for a, keep in _HELD:
+            a.max_ctas = HELD_MAX_CTAS
+        _DEFERRED.extend(_HELD)
+        _HELD.clear()
     if not _DEFERRED:
         return
     side = _side_stream()
@@ -236,28 +245,32 @@ def flush_wgrads():
         if TIMELINE is not None:
             e1.record(side)
             TIMELINE.append(('wgrad3x3', f'{a.frames}x{a.H} act{a.act_channels} dz{a.dz_channels}', 'side', e0, e1))
-        for t in keep:
-            t.record_stream(side)      # the caching allocator must not hand these buffers out again before the side stream is done
+        _INFLIGHT.append(keep)         # operands stay referenced until join_wgrads(): the caching allocator cannot hand them out again while
+                                       # the side stream reads them (record_stream would work too, but makes block re-use -- and with it
+                                       # cudaMalloc calls in steady state -- depend on event timing)
     _DEFERRED.clear()
     _SIDE_BUSY[0] = True
 
 
 def join_wgrads():
     """The current stream waits for every weight-gradient launch recorded so far."""
-    flush_wgrads()
+    flush_wgrads(held=True)
     if _SIDE_BUSY[0]:
         torch.cuda.current_stream().wait_stream(_side_stream())
         _SIDE_BUSY[0] = False
+    _INFLIGHT.clear()              # later work on this stream is ordered behind the side stream: the buffers may be re-used
 
 
 @profiled('wgrad3x3')
 def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0, map4=0, phase_channels=0,
-             strides=None, dw_offset=0, alg_scale=1.0, defer=False):
+             strides=None, dw_offset=0, alg_scale=1.0, defer=False, hold=False):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
 
     act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...).
     defer=True (the engine's backward): the launch is only recorded and issued on the weight-gradient stream by flush_wgrads();
-    the caller must join_wgrads() before dw is read."""
+    the caller must join_wgrads() before dw is read. hold=True (with defer): the launch waits for flush_wgrads(held=True) -- the
+    decoder's low-resolution layers, whose batch-norm backward is too short to hide them, are issued at the END of the decoder backward
+    with a reduced grid so that they fill the SMs left idle by the few-CTA latent / inference-network backward kernels that follow."""
     a = _lib.Wgrad3x3Args()
     assert act.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and dw.dtype == torch.float32
     a.act = ptr(act)
@@ -276,7 +289,7 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
         a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
     a.map4, a.phase_channels = map4, phase_channels
     if defer and WGRAD_STREAM and PROFILE is None and not torch.cuda.is_current_stream_capturing():
-        _DEFERRED.append((a, (act, dz, dw)))
+        (_HELD if hold and DEFER_JOIN else _DEFERRED).append((a, (act, dz, dw)))
     else:
         check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
     fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
