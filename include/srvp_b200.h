@@ -84,6 +84,13 @@ typedef struct {
                              epilogue thread owns a pixel, so lanes read consecutive 16-byte pieces of a plane) */
   int32_t add_frames;
   float* out_raw_f32;     /* optional fp32 copy of the raw result in the same [cout/4][frames*H*W][4] layout; `out` may then be NULL */
+  /* The same split with the per-video term fed through the TENSOR CORE instead of the epilogue: the per-video launch stores its fp32
+   * result as two bf16 tensors (out_hilo: hi = bf16(v) at channel c, lo = bf16(v - hi) at channel cout + c of `out`, pitch >= 2*cout;
+   * hi + lo carries 16 mantissa bits), and the per-frame launch reads that tensor as a second source (frame_map = video of the frame)
+   * whose 2*cout/64 K stages use the centre tap only (tap_mask 0x010) against identity weights. a_out_channels limits the copy of
+   * the conv input to the leading channels (the real input). */
+  int32_t out_hilo;
+  int32_t a_out_channels; /* 0 = all K stages are copied to a_out */
 } srvp_conv3x3_args;
 
 /* Number of rows of stats_partial srvp_conv3x3 writes for this geometry / channel count (= its persistent grid size). */
@@ -140,6 +147,13 @@ typedef struct {
   /* 0 = one CTA per SM; > 0 = at most this many CTAs, so that a launch issued on a second stream leaves SMs free for the
    * latency-bound kernels of the critical path it runs next to (srvp_b200/ops.py: weight-gradient stream). */
   int32_t max_ctas;
+  /* Optional batch-norm affine + LeakyReLU applied to `act` on the way in: act is then the RAW output z of the producing block and
+   * a = lrelu(z * scale + shift) is what gets multiplied (the decoder's last layer, module/conv.py:352-354: the forward pass does not
+   * store an activated copy). Only the thin weight-gradient kernel (64 activation channels x <= 4 real dz channels at 64x64,
+   * csrc/thin.cu) supports it; other shapes are rejected. */
+  const float* act_scale;
+  const float* act_shift;
+  int32_t act_lrelu;
 } srvp_wgrad3x3_args;
 int srvp_wgrad3x3(const srvp_wgrad3x3_args* args, void* stream);
 

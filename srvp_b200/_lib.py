@@ -30,13 +30,13 @@ class Conv3x3Args(ctypes.Structure):
                 ('cout', c_int), ('cout_padded', c_int), ('epilogue', c_int), ('out', c_ptr), ('out_cpitch', c_int),
                 ('out_coff', c_int), ('stats_partial', c_ptr), ('out_f32_nchw', c_ptr), ('a_out', c_ptr), ('a_out_cpitch', c_int),
                 ('out_row_pitch', c_int), ('out_xstride', c_int), ('sigmoid_d2s', c_int), ('tap_mask', ctypes.c_uint16 * CONV_MAX_STAGES),
-                ('add_f32', c_ptr), ('add_frames', c_int), ('out_raw_f32', c_ptr)]
+                ('add_f32', c_ptr), ('add_frames', c_int), ('out_raw_f32', c_ptr), ('out_hilo', c_int), ('a_out_channels', c_int)]
 
 
 class Wgrad3x3Args(ctypes.Structure):
     _fields_ = [('act', c_ptr), ('act_channels', c_int), ('act_cpitch', c_int), ('act_coff', c_int), ('dz', c_ptr),
                 ('dz_channels', c_int), ('dz_cpitch', c_int), ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
-                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int), ('map4', c_int), ('phase_channels', c_int), ('max_ctas', c_int)]
+                ('dw', c_ptr), ('stride_cout', c_i64), ('stride_cin', c_i64), ('flip', c_int), ('map4', c_int), ('phase_channels', c_int), ('max_ctas', c_int), ('act_scale', c_ptr), ('act_shift', c_ptr), ('act_lrelu', c_int)]
 
 
 class BnBwdArgs(ctypes.Structure):

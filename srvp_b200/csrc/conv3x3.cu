@@ -58,6 +58,8 @@ struct ConvDev {
   const float* add;                // optional fp32 (add_frames, H, W, cout) tensor added to the accumulators of frame f % add_frames
   int add_frames;
   float* out_raw_f32;              // optional: the raw result is (also) stored as fp32 (F, H, W, cout)
+  int out_hilo;                    // the fp32 result is stored as TWO bf16 tensors: hi = bf16(v) at channel c, lo = bf16(v - hi) at cout + c
+  int a_out_stages;                // K stages copied to a_out (the leading ones; 0 = all)
   int out_row_pitch, out_xstride;  // output pixel index = (f*H + y)*out_row_pitch + x*out_xstride (dense: W, 1)
   int sig_d2s;                     // sigmoid epilogue: columns are (py,px,c) sub-pixel phases of a (F, cout/4, 2H, 2W) image
   int masked;                      // any K stage with fewer than nine taps (4x4 stride-2 family)
@@ -176,8 +178,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mtile = tile / p.num_nblk;
       const long long vbase = (long long)mtile * MT - p.Wp - 1;
-      const bool store_a = p.a_out != nullptr && (tile % p.num_nblk) == 0;
+      const bool store_tile = p.a_out != nullptr && (tile % p.num_nblk) == 0;
       for (int s = 0; s < p.nstages; ++s, ++it) {
+        const bool store_a = store_tile && s < p.a_out_stages;
         const int hs = it % kHaloStages;
         const bool second = s >= p.stages0;
         const SrcDev& sd = p.src[second ? 1 : 0];
@@ -371,6 +374,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mtile = tile / p.num_nblk, nblk = tile % p.num_nblk;
       const int as = tcount % C::ACC_STAGES;
+      if constexpr (EPI == SRVP_EPI_RAW_BF16) {
+        if (p.add != nullptr && (lane & 7) == 0) {
+          // The per-video addend is fetched by the thread that owns the row, batch after batch (8 dependent round trips per 512-row
+          // tile): from HBM each costs ~1 us and the epilogue, not the MMAs, paces the layer (+1.1 ms on the 64-channel 64x64 layer,
+          // profiles/r03k_fwd_ablate.log). Pull the addend of this CTA's NEXT tile into L2 now -- one full epilogue of lead time; 8 lanes
+          // share a 128-byte line of a channel-group plane, so every 8th lane asks for it.
+          const int ntile = tile + gridDim.x;
+          if (ntile < total_tiles) {
+            const int nmt = ntile / p.num_nblk, nnb = ntile % p.num_nblk;
+            const size_t npix = (size_t)p.add_frames * p.H * p.W;
+#pragma unroll 1
+            for (int mb = 0; mb < C::MBLK; ++mb) {
+              const long long v = (long long)nmt * MT + mb * 128 + tid;
+              int f = 0, y = 0, x = 0;
+              if (decode_vpix(v, p.vtotal, HpWp, p.Wp, p.H, p.W, f, y, x)) {
+                const float4* ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nnb * NB) >> 2) * npix + (size_t)(((f % p.add_frames) * p.H + y) * p.W + x);
+#pragma unroll
+                for (int q = 0; q < NB / 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)q * npix));
+              }
+            }
+          }
+        }
+      }
       mbar_wait(&acc_full[as], (tcount / C::ACC_STAGES) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + as * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
@@ -411,6 +437,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           rowpix[tid] = valid ? ((f * p.H + y) * p.out_row_pitch + x * p.out_xstride) : -1;
           uint8_t* srow = staging + (size_t)tid * C::STAGE_PITCH;
           constexpr int BPP = C::STAGE_COLS / 32;  // 32-column batches per staging pass
+          // out_hilo: every column block is stored twice, first hi = bf16(v), then lo = bf16(v - hi), `cout` channels further
+          const int npass = p.out_hilo ? 2 : 1;
+#pragma unroll 1
+          for (int hl = 0; hl < npass; ++hl)
 #pragma unroll
           for (int ps = 0; ps < NB / C::STAGE_COLS; ++ps) {
 #pragma unroll
@@ -418,6 +448,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               const int bi = ps * BPP + bb;
               float vals[32];
               tmem_ld32(acc + mb * NB + bi * 32, vals);
+              if (hl == 1) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) vals[q] -= __bfloat162float(__float2bfloat16(vals[q]));
+              }
               // The fp32 per-video tensor (written through out_raw_f32 by one launch, added through `add` by another) is laid out as
               // [cout / 4][frames * H * W][4]: the epilogue thread owns a ROW (pixel), so consecutive lanes = consecutive pixels read /
               // write consecutive 16-byte pieces of one channel-group plane -- coalesced. In the pixel-major (frames, H, W, cout)
@@ -447,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<uint4*>(srow + bb * 64 + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
-            if (mb == C::MBLK - 1 && ps == NB / C::STAGE_COLS - 1) {
+            if (mb == C::MBLK - 1 && ps == NB / C::STAGE_COLS - 1 && hl == npass - 1) {
               tc_fence_before();
               mbar_arrive(&acc_empty[as]);
             }
@@ -473,12 +507,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             constexpr int LPR = C::STAGE_COLS / 8;  // lanes per row (16 B each)
             constexpr int RPI = 32 / LPR;           // rows per warp instruction
             const int lrow = lane / LPR, lcol = lane % LPR;
-            const int cbase = nblk * NB + ps * C::STAGE_COLS + lcol * 8;
+            const int cbase = nblk * NB + ps * C::STAGE_COLS + lcol * 8 + hl * p.cout;
 #pragma unroll 4
             for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += RPI) {
               const int r = r0 + lrow;
               const int pix = rowpix[r];
-              if (pix >= 0 && cbase < p.cout && p.out != nullptr && !(p.dbg & 4)) {
+              if (pix >= 0 && cbase < p.cout * npass && p.out != nullptr && !(p.dbg & 4)) {
                 const uint4 val = *reinterpret_cast<const uint4*>(staging + (size_t)r * C::STAGE_PITCH + lcol * 16);
                 *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_cpitch + p.out_coff + cbase) = val;
               }
@@ -637,6 +671,16 @@ int launch(ConvDev& d, cudaStream_t stream, int num_sms) {
 }  // namespace
 
 int num_sms_cached();
+int thin_conv_grid(int frames);                                                    // thin.cu
+bool thin_conv_eligible(const srvp_conv3x3_args* a);
+int thin_conv_launch(const srvp_conv3x3_args* a, cudaStream_t stream);
+
+// shape for which the thin-input kernel of thin.cu (and its grid = number of statistics rows) is used
+static bool thin_shape(int H, int W, int cout_padded, int kin_total) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SRVP_THIN"); on = e ? atoi(e) : 1; }
+  return on && H == 64 && W == 64 && cout_padded == 64 && kin_total == 16;
+}
 
 }  // namespace srvp
 
@@ -645,6 +689,7 @@ using namespace srvp;
 extern "C" int srvp_conv3x3_nblock(int32_t cout_padded) { return choose(cout_padded).NB; }
 
 extern "C" int srvp_conv3x3_num_mtiles(int32_t frames, int32_t H, int32_t W, int32_t cout_padded, int32_t kin_total) {
+  if (thin_shape(H, W, cout_padded, kin_total)) return thin_conv_grid(frames);
   const Choice c = choose(cout_padded, kin_total);
   const long long vtotal = (long long)frames * (H + 1) * (W + 2);
   const long long tiles = ((vtotal + c.MT - 1) / c.MT) * (cout_padded / c.NB);
@@ -658,6 +703,13 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   SRVP_REQUIRE(a->nsrc == 1 || a->nsrc == 2, "conv3x3: nsrc must be 1 or 2");
   int kin_total = 0;
   for (int i = 0; i < a->nsrc; ++i) kin_total += a->src[i].channels;
+  if (thin_shape(a->H, a->W, a->cout_padded, kin_total)) {
+    if (thin_conv_eligible(a)) return thin_conv_launch(a, stream);
+    // not expressible by the thin kernel (fused source transform, saved input, ...): the generic kernel below writes fewer statistics
+    // rows than srvp_conv3x3_num_mtiles() announced for this shape -- the remaining rows must read as zeros
+    if (a->stats_partial != nullptr)
+      cudaMemsetAsync(a->stats_partial, 0, (size_t)thin_conv_grid(a->frames) * a->cout * 2 * sizeof(float), stream);
+  }
   const Choice ch = choose(a->cout_padded, kin_total);
   SRVP_REQUIRE(a->cout_padded % ch.NB == 0 && a->cout <= a->cout_padded, "conv3x3: bad cout %d / padded %d", a->cout, a->cout_padded);
   const int kper = (a->src[0].channels == 16 && a->nsrc == 1) ? 16 : 64;
@@ -697,6 +749,15 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   d.add = a->add_f32;
   d.add_frames = a->add_frames;
   d.out_raw_f32 = a->out_raw_f32;
+  d.out_hilo = a->out_hilo;
+  if (a->out_hilo)
+    SRVP_REQUIRE(a->epilogue == SRVP_EPI_RAW_BF16 && a->out != nullptr && a->cout % 64 == 0 && a->cout == a->cout_padded && a->stats_partial == nullptr &&
+                 a->out_cpitch >= a->out_coff + 2 * a->cout, "conv3x3: hi/lo output needs cout %% 64 == 0, no statistics and a channel pitch of 2*cout");
+  d.a_out_stages = nst;
+  if (a->a_out && a->a_out_channels > 0) {
+    SRVP_REQUIRE(a->a_out_channels % kper == 0 && a->a_out_channels <= nst * kper, "conv3x3: bad a_out_channels %d", a->a_out_channels);
+    d.a_out_stages = a->a_out_channels / kper;
+  }
   if (a->add_f32 || a->out_raw_f32)
     SRVP_REQUIRE(a->epilogue == SRVP_EPI_RAW_BF16 && a->cout % 64 == 0 && a->cout == a->cout_padded && (a->add_f32 == nullptr || a->add_frames > 0),
                  "conv3x3: add / fp32 output need cout %% 64 == 0 (cout %d) and add_frames > 0", a->cout);
@@ -716,7 +777,7 @@ extern "C" int srvp_conv3x3(const srvp_conv3x3_args* a, void* stream_) {
   }
   if (d.masked) SRVP_REQUIRE(kper == 64, "conv3x3: tap masks need 64-channel stages");
   if (d.sig_d2s) SRVP_REQUIRE(a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32 && a->cout % 4 == 0, "conv3x3: sigmoid_d2s needs cout = 4*nc");
-  if (a->a_out) SRVP_REQUIRE(a->a_out_cpitch % 8 == 0 && a->a_out_cpitch >= nst * kper, "conv3x3: a_out pitch %d too small", a->a_out_cpitch);
+  if (a->a_out) SRVP_REQUIRE(a->a_out_cpitch % 8 == 0 && a->a_out_cpitch >= d.a_out_stages * kper, "conv3x3: a_out pitch %d too small", a->a_out_cpitch);
   const int sms = num_sms_cached();
   if (a->epilogue == SRVP_EPI_SIGMOID_NCHW_F32) {
     SRVP_REQUIRE(ch.NB == 16 && kper == 64 && a->out_f32_nchw != nullptr, "conv3x3: sigmoid epilogue needs cout<=16, 64-channel stages");

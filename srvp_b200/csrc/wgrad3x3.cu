@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3x3_kernel(const WgradDev 
 
 int num_sms_cached();
 int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream);   // wgrad3x3_tma.cu
+int thin_wgrad_try(const srvp_wgrad3x3_args* a, cudaStream_t stream);     // thin.cu
 
 }  // namespace srvp
 
@@ -288,7 +289,13 @@ extern "C" int srvp_wgrad3x3(const srvp_wgrad3x3_args* a, void* stream_) {
   // 3x3 layers whose operands are multiples of 64 channels take the TMA-fed kernel (wgrad3x3_tma.cu); thin operands (the first
   // encoder / last decoder layer) and the 4x4 stride-2 family stay on the cp.async kernel below
   {
-    const int r = wgrad3x3_tma_try(a, stream);
+    // thin operand at 64x64 (first encoder block / decoder head): the im2col kernel of thin.cu
+    int r = thin_wgrad_try(a, stream);
+    if (r != 0) return r < 0 ? r : 0;
+    SRVP_REQUIRE(a->act_scale == nullptr && a->act_shift == nullptr && a->act_lrelu == 0,
+                 "wgrad3x3: an activation transform is only supported by the thin 64x64 kernel (act %d x dz %d channels at %dx%d)", a->act_channels,
+                 a->dz_channels, a->H, a->W);
+    r = wgrad3x3_tma_try(a, stream);
     if (r != 0) return r < 0 ? r : 0;
   }
   WgradDev d{};

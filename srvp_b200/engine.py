@@ -184,9 +184,15 @@ def _encoder_bwd(enc, c, d_hx, skip_handle):
     dz_last = ops.bn_tanh_rows_bwd(d_hx.contiguous(), c.hx, c.z_last, bn_l.weight, c.st_last, grads[gi + 1], grads[gi + 2],
                                    sync=ops.is_sync_bn(bn_l))
     # weight gradient: dWl[co, (y,x,c)] = sum_f dz_last[f, co] * a_last[f, (y,x,c)]
-    dwl = torch.zeros(enc.nh, 16, C, dtype=torch.float32, device=dev)
-    ops.gemm(dz_last.t(), c.a_last.view(F_, 16 * C).t(), dwl.view(enc.nh, 16 * C), accumulate=True)
-    ops.transpose_last2(dwl, out=grads[gi])
+    def head_wgrad():
+        dwl = torch.zeros(enc.nh, 16, C, dtype=torch.float32, device=dev)
+        ops.gemm(dz_last.t(), c.a_last.view(F_, 16 * C).t(), dwl.view(enc.nh, 16 * C), accumulate=True)
+        ops.transpose_last2(dwl, out=grads[gi])
+    if direct[gi]:     # nobody reads it before the optimizer: off the critical path (ops.side_section)
+        with ops.side_section(dz_last, c.a_last):
+            head_wgrad()
+    else:
+        head_wgrad()
     # data gradient w.r.t. the pooled activation: (F, 4, 4, C)
     da = torch.empty(F_, 4, 4, C, dtype=torch.bfloat16, device=dev)
     ops.gemm(dz_last, c.wl.view(enc.nh, 16 * C).t(), da.view(F_, 16 * C))
@@ -265,6 +271,11 @@ class _DecCtx:
     pass
 
 
+# Split skip convolutions at or above this resolution add the per-video term as extra K stages ([hi | lo] bf16 x identity weights) instead
+# of in the epilogue. OFF by default: measured slower (64x64 layer 3.00 vs 2.49 ms, 32x32 1.88 vs 1.37 ms; step 56.7 vs 55.3 ms,
+# profiles/r03x_*): a tile then has three loader stages, each a full cp.async round trip, and only two halo buffers to hide them in.
+ADD_HILO_MIN_RES = int(__import__('os').environ.get('SRVP_ADD_HILO_MIN_RES', '1000'))
+THIN_HEAD_WGRAD = int(__import__('os').environ.get('SRVP_THIN', '1'))   # decoder head: weight gradient from the raw z (csrc/thin.cu)
 HOLD_RES = int(__import__('os').environ.get('SRVP_WGRAD_HOLD_RES', '16'))   # decoder layers at or below this resolution: weight gradients held back
 
 
@@ -318,10 +329,22 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
             nvid = sel.shape[0]
             s_src = _skip_src(skip_levels[blk.skip_level], sel)
             wp_s = ops.pack_conv3x3(blk.conv.weight, 'conv', cin_range=(h_src.channels, s_src.channels))
-            rs = ops.conv3x3([s_src], wp_s, nvid, blk.res, blk.res, blk.cout, out_f32=True, save_input=training, alg_scale=0.0)
             wp_h = ops.pack_conv3x3(blk.conv.weight, 'conv', cin_range=(0, h_src.channels))
-            r = ops.conv3x3([h_src], wp_h, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training, add=rs[0],
-                            alg_scale=(h_src.channels + s_src.channels) / h_src.channels)
+            alg = (h_src.channels + s_src.channels) / h_src.channels
+            if blk.res >= ADD_HILO_MIN_RES:
+                # per-video term through the TENSOR CORE: stored as [hi | lo] bf16, read by the per-frame launch as a second source whose K
+                # stages multiply the centre tap only against identity weights (+22 % MMAs); ablation switch, see ADD_HILO_MIN_RES
+                rs = ops.conv3x3([s_src], wp_s, nvid, blk.res, blk.res, blk.cout, out_hilo=True, save_input=training, alg_scale=0.0)
+                if getattr(c, 'vid_map', None) is None:     # decoder frame (t, b) -> video b
+                    c.vid_map = torch.arange(nvid, dtype=torch.int32, device=dev).repeat(F_ // nvid)
+                hl_src = Src(rs[0], 2 * blk.cout, None, None, c.vid_map, 0, SRC_DIRECT, False)
+                wp = ops.concat_packs([wp_h, ops.hilo_identity_pack(blk.cout, dev)], blk.cout)
+                masks = [0x1ff] * (h_src.channels // 64) + [0x010] * (2 * blk.cout // 64)
+                r = ops.conv3x3([h_src, hl_src], wp, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training, tap_masks=masks,
+                                a_out_channels=h_src.channels, cin_real=h_src.channels, alg_scale=alg)
+            else:
+                rs = ops.conv3x3([s_src], wp_s, nvid, blk.res, blk.res, blk.cout, out_f32=True, save_input=training, alg_scale=0.0)
+                r = ops.conv3x3([h_src], wp_h, F_, blk.res, blk.res, blk.cout, stats=training, save_input=training, add=rs[0], alg_scale=alg)
             c.split[li] = (rs[2] if training else None, s_src.channels, nvid)
         else:
             srcs = [h_src]
@@ -342,7 +365,8 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
     c.final_src = Src(prev.tensor, prev.channels, prev.scale, prev.shift, None, 0, SRC_DIRECT, True)
     if final.in_channels == 64 and final.out_channels <= 3 and tuple(prev.tensor.shape[1:]) == (64, 64, 64):
         # dedicated head kernel (csrc/head.cu): activation + tap-expanded 64 -> nc transposed convolution + sigmoid
-        c.x_hat, c.final_a = ops.decoder_head_fwd(c.final_src, final.weight, F_, final.out_channels, save_input=training)
+        # no activated copy is stored for the weight gradient: the thin weight-gradient kernel (csrc/thin.cu) activates the raw z itself
+        c.x_hat, c.final_a = ops.decoder_head_fwd(c.final_src, final.weight, F_, final.out_channels, save_input=training and not THIN_HEAD_WGRAD)
     else:
         wp = ops.pack_conv3x3(final.weight, 'convT')
         r = ops.conv3x3([c.final_src], wp, F_, 64, 64, final.out_channels, sigmoid_nchw=True, save_input=training)
@@ -365,7 +389,12 @@ def _decoder_bwd(dec, c, d_xhat, skip_handle):
     final = dec.conv[3][1]
     nc = final.out_channels
     dz = ops.sigmoid_bwd(d_xhat.contiguous(), c.x_hat)  # (F,64,64,16)
-    ops.wgrad3x3(c.final_a, final.in_channels, dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT', defer=True)
+    if c.final_a is None:
+        fs = c.final_src
+        ops.wgrad3x3(fs.tensor, final.in_channels, dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT', defer=True,
+                     act_affine=(fs.scale, fs.shift, fs.lrelu))
+    else:
+        ops.wgrad3x3(c.final_a, final.in_channels, dz, 16, F_, 64, 64, nc, final.in_channels, grads[-1], 'convT', defer=True)
     wp = ops.pack_conv3x3(final.weight, 'convT_dgrad')
     da, _ = ops.conv3x3([Src(dz, 16)], wp, F_, 64, 64, final.in_channels, cin_real=nc)
     da_mode, da_coff = SRC_DIRECT, 0
@@ -412,9 +441,15 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads, direct):
     dz0 = ops.bn_bwd(c.z0, c.st0, up_bn.weight, grads[1], grads[2], da, da_mode, F_, 4, 4, C0, da_coff=0, sync=ops.is_sync_bn(up_bn))
     d_inp = torch.empty(F_, nin, dtype=torch.float32, device=dev)
     ops.gemm(dz0.view(F_, 16 * C0), c.wp0.view(nin, 16 * C0), d_inp, det_split=8 if (16 * C0) % (8 * 64) == 0 else 0)
-    dwp = torch.zeros(nin, 16, C0, dtype=torch.float32, device=dev)
-    ops.gemm(c.dec_inp.t(), dz0.view(F_, 16 * C0).t(), dwp.view(nin, 16 * C0), accumulate=True)
-    ops.transpose_last2(dwp, out=grads[0])
+    def head_wgrad():
+        dwp = torch.zeros(nin, 16, C0, dtype=torch.float32, device=dev)
+        ops.gemm(c.dec_inp.t(), dz0.view(F_, 16 * C0).t(), dwp.view(nin, 16 * C0), accumulate=True)
+        ops.transpose_last2(dwp, out=grads[0])
+    if direct[0]:      # nobody reads it before the optimizer: off the critical path (ops.side_section)
+        with ops.side_section(c.dec_inp, dz0):
+            head_wgrad()
+    else:
+        head_wgrad()
     # The decoder's weight gradients may keep running under the latent / inference-network backward (few-CTA, latency-bound kernels)
     # when every gradient lives in the GradBucket (consumed only after allreduce_mean() / Adam.step(), which join) and no early
     # all-reduce of the decoder segment is about to read them; otherwise they must be final here.

@@ -107,26 +107,40 @@ def latent_bwd(p_z, dynamics, fwd, g_y_all, g_res, g_pz, nt, os_, dt, nh):
     B, ny = g_y_all.shape[1], g_y_all.shape[2]
     out = _latent_bwd_kernel(p_z, dynamics, fwd, g_y_all.contiguous(), g_res.contiguous(), g_pz.contiguous(), nt, os_, dt, nh)
 
-    def mlp_grads(linears, x0, hid, dpre_hidden, dpre_last):
+    def mlp_grads(linears, x0, hid, dpre_hidden, dpre_last, targets, direct):
         grads = []
         L = len(linears)
         rows = x0.shape[0]
         for l, lin in enumerate(linears):
             inp = x0 if l == 0 else hid[l - 1].reshape(rows, nh)
             dp = dpre_last if l == L - 1 else dpre_hidden[l].reshape(rows, nh)
-            dW = torch.zeros_like(lin.weight)
+            dW, db = targets[2 * l], targets[2 * l + 1]
             ops.gemm(dp.t(), inp.t(), dW, accumulate=True)
-            db = torch.zeros_like(lin.bias)
             colsum(dp, db)
-            grads.append((dW, db))
+            grads.append((None if direct[2 * l] else dW, None if direct[2 * l + 1] else db))
         return grads
 
     # inputs of the first layers (fp32): dynamics sees cat[y_s, z_frame(s)], p_z sees y at the first sub-step of each frame
     y_all, z = fwd['y_all'], fwd['z']
     x0_d = torch.cat([y_all[:S], z.repeat_interleave(os_, dim=0)], 2).reshape(S * B, -1)
     x0_p = y_all[0:S:os_].reshape((nt - 1) * B, ny)
-    g_d = mlp_grads(dynamics, x0_d, fwd['hid_d'], out['dpre_d'], out['dout_d'].reshape(S * B, ny))
-    g_p = mlp_grads(p_z, x0_p, fwd['hid_p'], out['dpre_p'], g_pz.reshape((nt - 1) * B, -1))
+    # The eight weight-gradient GEMMs + bias column sums are read by nobody before the optimizer: under a GradBucket they go to the
+    # weight-gradient stream (ops.side_section) and leave the critical path (latent loop -> inference networks -> encoder backward).
+    pairs_d = [ops.grad_target(t) for lin in dynamics for t in (lin.weight, lin.bias)]
+    pairs_p = [ops.grad_target(t) for lin in p_z for t in (lin.weight, lin.bias)]
+    all_direct = all(d for _, d in pairs_d + pairs_p)
+    dout_d, g_pz2 = out['dout_d'].reshape(S * B, ny), g_pz.reshape((nt - 1) * B, -1)
+
+    def run():
+        gd = mlp_grads(dynamics, x0_d, fwd['hid_d'], out['dpre_d'], dout_d, [t for t, _ in pairs_d], [d for _, d in pairs_d])
+        gp = mlp_grads(p_z, x0_p, fwd['hid_p'], out['dpre_p'], g_pz2, [t for t, _ in pairs_p], [d for _, d in pairs_p])
+        return gp, gd
+
+    if all_direct:
+        with ops.side_section(x0_d, x0_p, fwd['hid_d'], fwd['hid_p'], out['dpre_d'], out['dpre_p'], dout_d, g_pz2):
+            g_p, g_d = run()
+    else:
+        g_p, g_d = run()
     return out['d_y0'], out['d_z'], g_p, g_d
 
 

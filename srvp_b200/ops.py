@@ -1,4 +1,5 @@
 """Tensor-level wrappers over the C ABI (include/srvp_b200.h). No arithmetic happens in Python."""
+import contextlib
 import ctypes
 import os
 from dataclasses import dataclass
@@ -28,7 +29,7 @@ def profiled(name):
                 e0.record()
                 out = fn(*args, **kwargs)
                 e1.record()
-                TIMELINE.append((name, PROFILE_TAG, 'main', e0, e1))
+                TIMELINE.append((name, PROFILE_TAG, 'side' if torch.cuda.current_stream() in _SIDE_STREAMS.values() else 'main', e0, e1))
                 return out
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -156,6 +157,30 @@ def pack_conv3x3(weight, kind, out=None, cin_range=None):
     return out
 
 
+_IDENT_PACKS = {}
+
+
+def hilo_identity_pack(cout, device):
+    """Packed weights of the K stages that feed a [hi | lo] bf16 per-video term through the tensor core: a (cout, 2*cout, 3, 3) weight
+    whose centre tap is [I | I] (every other tap is never loaded: tap mask 0x010). Built once per (cout, device)."""
+    key = (cout, str(device))
+    wp = _IDENT_PACKS.get(key)
+    if wp is None:
+        e = torch.zeros(cout, 2 * cout, 3, 3, dtype=torch.float32, device=device)
+        idx = torch.arange(cout, device=device)
+        e[idx, idx, 1, 1] = 1.0
+        e[idx, idx + cout, 1, 1] = 1.0
+        wp = _IDENT_PACKS[key] = pack_conv3x3(e, 'conv')
+    return wp
+
+
+def concat_packs(packs, cout):
+    """Packed operands of several input-channel ranges of one convolution -> one operand whose K stages are theirs back to back
+    (layout [N block][stage][tap][chunk][n][8]: the stages of a block are contiguous)."""
+    nblk = padded_n(cout) // lib().srvp_conv3x3_nblock(c_int(padded_n(cout)))
+    return torch.cat([p.view(nblk, -1) for p in packs], 1).reshape(-1)
+
+
 def _fill_src(cs, s):
     assert s.tensor.dtype == torch.bfloat16
     cs.ptr = ptr(s.tensor)
@@ -207,6 +232,7 @@ _HELD = []            # same, for launches that wait for flush_wgrads(held=True)
 HELD_MAX_CTAS = int(os.environ.get('SRVP_WGRAD_HELD_CTAS', '128'))
 _INFLIGHT = []
 _SIDE_BUSY = [False]
+SIDE_LAUNCHES = [0]   # weight-gradient launches issued on the side stream so far (tests)
 DEFER_JOIN = False    # set by parallel.GradBucket: gradients are only consumed after allreduce_mean() / Adam.step()
 
 
@@ -245,10 +271,30 @@ def flush_wgrads(held=False):
         if TIMELINE is not None:
             e1.record(side)
             TIMELINE.append(('wgrad3x3', f'{a.frames}x{a.H} act{a.act_channels} dz{a.dz_channels}', 'side', e0, e1))
+        SIDE_LAUNCHES[0] += 1
         _INFLIGHT.append(keep)         # operands stay referenced until join_wgrads(): the caching allocator cannot hand them out again while
                                        # the side stream reads them (record_stream would work too, but makes block re-use -- and with it
                                        # cudaMalloc calls in steady state -- depend on event timing)
     _DEFERRED.clear()
+    _SIDE_BUSY[0] = True
+
+
+@contextlib.contextmanager
+def side_section(*keep):
+    """`with side_section(tensors...) as on_side:` -- launches inside run on the weight-gradient stream (behind everything enqueued on the
+    current stream so far) when every consumer of their results joins first, i.e. under a GradBucket (DEFER_JOIN); otherwise inline
+    (on_side False). For parameter-gradient work that nothing on the critical path of the backward pass reads: the body must write
+    only into buffers that outlive it (ops.grad_target views) and `keep` must list the tensors it reads."""
+    if not (WGRAD_STREAM and DEFER_JOIN and PROFILE is None) or torch.cuda.is_current_stream_capturing():
+        yield False
+        return
+    side = _side_stream()
+    ev = torch.cuda.Event()
+    ev.record()
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        yield True
+    _INFLIGHT.append(keep)
     _SIDE_BUSY[0] = True
 
 
@@ -263,10 +309,11 @@ def join_wgrads():
 
 @profiled('wgrad3x3')
 def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, kind, dz_coff=0, act_coff=0, map4=0, phase_channels=0,
-             strides=None, dw_offset=0, alg_scale=1.0, defer=False, hold=False):
+             strides=None, dw_offset=0, alg_scale=1.0, defer=False, hold=False, act_affine=None):
     """dw (fp32, the nn.Conv2d / nn.ConvTranspose2d weight layout) += weight gradient. kind: 'conv' | 'convT'.
 
-    act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...).
+    act: materialised conv input (frames, H, W, >=act_channels) bf16 as written by conv3x3(..., a_out=...); or, with
+    act_affine = (scale, shift, lrelu), the RAW output of the producing block, activated on the way in (decoder head only, csrc/thin.cu).
     defer=True (the engine's backward): the launch is only recorded and issued on the weight-gradient stream by flush_wgrads();
     the caller must join_wgrads() before dw is read. hold=True (with defer): the launch waits for flush_wgrads(held=True) -- the
     decoder's low-resolution layers, whose batch-norm backward is too short to hide them, are issued at the END of the decoder backward
@@ -288,8 +335,13 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
     else:
         a.stride_cout, a.stride_cin, a.flip = 9, cout * 9, 1
     a.map4, a.phase_channels = map4, phase_channels
+    keep = (act, dz, dw)
+    if act_affine is not None:
+        sc, sh, lr = act_affine
+        a.act_scale, a.act_shift, a.act_lrelu = ptr(sc), ptr(sh), int(lr)
+        keep = keep + (sc, sh)
     if defer and WGRAD_STREAM and PROFILE is None and not torch.cuda.is_current_stream_capturing():
-        (_HELD if hold and DEFER_JOIN else _DEFERRED).append((a, (act, dz, dw)))
+        (_HELD if hold and DEFER_JOIN else _DEFERRED).append((a, keep))
     else:
         check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
     fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
@@ -303,12 +355,14 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
 @profiled('conv3x3')
 def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_coff=0, stats=False, sigmoid_nchw=False, cin_real=None,
             save_input=False, tap_masks=None, out_row_pitch=0, out_xstride=0, stats_out=None, a_out=None, sigmoid_d2s=False, taps=9,
-            add=None, out_f32=False, alg_scale=1.0):
+            add=None, out_f32=False, alg_scale=1.0, out_hilo=False, a_out_channels=0):
     """Fused 3x3/s1/p1 convolution. Returns (out, stats_partial or None).
 
     4x4 stride-2 family (DCGAN64): tap_masks = one 9-bit mask per 64-channel K stage (or one int for all stages), out_row_pitch /
     out_xstride / out_coff address one sub-pixel phase of the output, stats_out / a_out are caller-allocated (shared by the four
-    phase launches), sigmoid_d2s scatters the (py,px,c) columns of the last layer to the NCHW image."""
+    phase launches), sigmoid_d2s scatters the (py,px,c) columns of the last layer to the NCHW image.
+    out_hilo: the fp32 result is stored as (frames, H, W, 2*cout) bf16 = [hi | lo] (see srvp_conv3x3_args.out_hilo); a_out_channels:
+    only the leading input channels are copied to a_out."""
     a = _lib.Conv3x3Args()
     a.nsrc = len(srcs)
     for i, s in enumerate(srcs):
@@ -344,7 +398,8 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
             a.out_cpitch = cout
         else:
             if out is None:
-                out = torch.empty(frames, H, W, cout, dtype=torch.bfloat16, device=dev)
+                out = torch.empty(frames, H, W, 2 * cout if out_hilo else cout, dtype=torch.bfloat16, device=dev)
+            a.out_hilo = int(out_hilo)
             a.out = ptr(out)
             a.out_cpitch = out.shape[-1] if out_cpitch is None else out_cpitch
             a.out_coff = out_coff
@@ -356,9 +411,9 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
             stats_partial = torch.empty(nmt, cout, 2, dtype=torch.float32, device=dev)
             a.stats_partial = ptr(stats_partial)
     if save_input and a_out is None:
-        a_out = torch.empty(frames, H, W, sum(s.channels for s in srcs), dtype=torch.bfloat16, device=dev)
+        a_out = torch.empty(frames, H, W, a_out_channels or sum(s.channels for s in srcs), dtype=torch.bfloat16, device=dev)
     if save_input:
-        a.a_out, a.a_out_cpitch = ptr(a_out), a_out.shape[-1]
+        a.a_out, a.a_out_cpitch, a.a_out_channels = ptr(a_out), a_out.shape[-1], a_out_channels
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
     cin_real = cin_real if cin_real is not None else sum(s.channels for s in srcs)
     obytes = (out.numel() * out.element_size()) if not out_xstride else 2.0 * frames * H * W * cout

@@ -446,3 +446,72 @@ def test_rsample_and_u8_input(dev):
     assert torch.equal(out.float(), bf(ref))
     x = ops.u8_to_tbchw_f32(v)
     assert torch.allclose(x, (v.float() / 255).permute(1, 0, 4, 2, 3), rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ thin operands at 64x64 (csrc/thin.cu)
+@pytest.mark.parametrize('nc,frames', [(3, 5), (1, 2), (3, 40)])
+def test_thin_conv_first_encoder_block(dev, nc, frames):
+    """Conv2d(nc, 64, 3, 1, 1) on the padded 16-channel image tensor through the im2col kernel (the shape engine._encoder_fwd launches: no
+    fused transform, no saved input): output, BN statistics rows (one per CTA, srvp_conv3x3_num_mtiles) and run-to-run determinism."""
+    from srvp_b200 import ops
+    torch.manual_seed(nc * 100 + frames)
+    x = torch.zeros(frames, 64, 64, 16, device=dev, dtype=torch.bfloat16)
+    x[..., :nc] = torch.rand(frames, 64, 64, nc, device=dev).to(torch.bfloat16)
+    w = torch.randn(64, nc, 3, 3, device=dev) * 0.2
+    ref = F.conv2d(x[..., :nc].float().permute(0, 3, 1, 2), bf(w), padding=1).permute(0, 2, 3, 1)
+    wp = ops.pack_conv3x3(w, 'conv')
+    out, st = ops.conv3x3([ops.Src(x, 16)], wp, frames, 64, 64, 64, stats=True, cin_real=nc)
+    assert st.shape[0] == ops.conv3x3_stats_rows(frames, 64, 64, 64, 16)
+    assert float((out.float() - ref).abs().max() / ref.abs().max()) < 1.5e-2
+    s = st.double().sum(0)
+    o = out.double()
+    s_ref = torch.stack([o.sum((0, 1, 2)), (o * o).sum((0, 1, 2))], 1)
+    assert float(((s - s_ref).abs() / (s_ref.abs() + 1)).max()) < 1e-3
+    out2, st2 = ops.conv3x3([ops.Src(x, 16)], wp, frames, 64, 64, 64, stats=True, cin_real=nc)
+    assert torch.equal(out, out2) and torch.equal(st, st2)
+
+
+def test_thin_conv_head_data_gradient(dev):
+    """Data gradient of ConvTranspose2d(64, nc, 3, 1, 1): the thin dz (16 padded channels) convolved back to 64 channels."""
+    from srvp_b200 import ops
+    frames, nc = 3, 3
+    dz = torch.zeros(frames, 64, 64, 16, device=dev, dtype=torch.bfloat16)
+    dz[..., :nc] = (torch.randn(frames, 64, 64, nc, device=dev) * 0.1).to(torch.bfloat16)
+    wt = torch.randn(64, nc, 3, 3, device=dev) * 0.2            # ConvTranspose2d weight (cin, cout, 3, 3)
+    a = torch.randn(frames, 64, 64, 64, device=dev, requires_grad=True)
+    y = F.conv_transpose2d(a.permute(0, 3, 1, 2), bf(wt), padding=1)
+    y.backward(dz[..., :nc].float().permute(0, 3, 1, 2))
+    da, _ = ops.conv3x3([ops.Src(dz, 16)], ops.pack_conv3x3(wt, 'convT_dgrad'), frames, 64, 64, 64, cin_real=nc)
+    assert float((da.float() - a.grad).abs().max() / a.grad.abs().max()) < 1.5e-2
+
+
+@pytest.mark.parametrize('nc,frames', [(3, 4), (1, 3), (3, 37)])
+def test_thin_wgrad_both_ends(dev, nc, frames):
+    """Weight gradients with a thin operand: the first encoder block (images thin, dz wide) and the decoder head (dz thin, activations
+    wide and computed on the way in from the raw z with its batch-norm affine + LeakyReLU) against torch autograd."""
+    from srvp_b200 import ops
+    torch.manual_seed(nc + frames)
+    # first encoder block: Conv2d(nc, 64)
+    x = torch.zeros(frames, 64, 64, 16, device=dev, dtype=torch.bfloat16)
+    x[..., :nc] = torch.rand(frames, 64, 64, nc, device=dev).to(torch.bfloat16)
+    dz = (torch.randn(frames, 64, 64, 64, device=dev) * 0.1).to(torch.bfloat16)
+    w = torch.zeros(64, nc, 3, 3, device=dev, requires_grad=True)
+    F.conv2d(x[..., :nc].float().permute(0, 3, 1, 2), w, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    dw = torch.zeros(64, nc, 3, 3, device=dev)
+    ops.wgrad3x3(x, 16, dz, 64, frames, 64, 64, 64, nc, dw, 'conv')
+    assert rel(dw, w.grad) < 2e-3
+    # decoder head: ConvTranspose2d(64, nc) over a = lrelu(z * scale + shift)
+    z = torch.randn(frames, 64, 64, 64, device=dev).to(torch.bfloat16)
+    sc, sh = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev) * 0.3
+    a = bf(F.leaky_relu(z.float() * sc + sh, 0.2))
+    dzt = torch.zeros(frames, 64, 64, 16, device=dev, dtype=torch.bfloat16)
+    dzt[..., :nc] = (torch.randn(frames, 64, 64, nc, device=dev) * 0.1).to(torch.bfloat16)
+    wt = torch.zeros(64, nc, 3, 3, device=dev, requires_grad=True)
+    F.conv_transpose2d(a.permute(0, 3, 1, 2), wt, padding=1).backward(dzt[..., :nc].float().permute(0, 3, 1, 2))
+    dwt = torch.zeros(64, nc, 3, 3, device=dev)
+    ops.wgrad3x3(z, 64, dzt, 16, frames, 64, 64, nc, 64, dwt, 'convT', act_affine=(sc, sh, True))
+    assert rel(dwt, wt.grad) < 2e-3
+    # the same head gradient from a materialised activation (no transform) must agree as well
+    dwt2 = torch.zeros(64, nc, 3, 3, device=dev)
+    ops.wgrad3x3(a.to(torch.bfloat16), 64, dzt, 16, frames, 64, 64, nc, 64, dwt2, 'convT')
+    assert rel(dwt2, wt.grad) < 2e-3

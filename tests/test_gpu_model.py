@@ -199,3 +199,40 @@ def test_batched_sample_rollout_decode_matches_per_sample(dev):
         for s in range(S):
             xs = m.decode(w, y[:, s * B:(s + 1) * B].contiguous(), skips)
             assert float(((xs - xb[:, s * B:(s + 1) * B]) ** 2).mean()) < 1e-5
+
+
+def test_weight_gradient_stream_matches_inline(dev):
+    """The step bench.py / train.py run (GradBucket: gradients accumulated in place, weight gradients recorded and issued on their own
+    stream, the decoder's low-resolution ones held back, joined by allreduce_mean() / Adam.step()) must produce the gradients of the
+    plain autograd path with everything on one stream. Differences: summation order of the split-K atomics only."""
+    from srvp_b200 import ops, parallel
+    g = load_golden('vgg_skip_nc3')
+    x = make_input(6, 8, g['cfg']['nc'], 5).to(dev)
+
+    def grads(bucketed, stream_on):
+        m = build_model(g['cfg'], g['res_gain'], g['seeds']['model']).to(dev).train()
+        old = (ops.WGRAD_STREAM, ops.DEFER_JOIN, parallel.ACTIVE_BUCKET)
+        ops.WGRAD_STREAM, ops.DEFER_JOIN = int(stream_on), False
+        try:
+            bucket = None
+            if bucketed:
+                bucket = parallel.GradBucket(list(m.parameters()), early=list(m.decoder.parameters()))
+                parallel.ACTIVE_BUCKET = bucket
+                bucket.zero()
+            torch.manual_seed(3)
+            loss = model_loss(m(x, 6, dt=0.5), x, g['loss_cfg'])[0]
+            n0 = ops.SIDE_LAUNCHES[0]
+            loss.backward()
+            assert (ops.SIDE_LAUNCHES[0] > n0) == bool(stream_on)
+            if bucketed:
+                bucket.allreduce_mean()        # joins the weight-gradient stream
+            torch.cuda.synchronize()
+            return {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        finally:
+            ops.WGRAD_STREAM, ops.DEFER_JOIN, parallel.ACTIVE_BUCKET = old
+
+    ref = grads(False, False)
+    for bucketed, stream_on in ((True, True), (False, True), (True, False)):
+        got = grads(bucketed, stream_on)
+        for n, r in ref.items():
+            assert rel_l2(got[n], r) < 2e-3, (bucketed, stream_on, n, rel_l2(got[n], r))

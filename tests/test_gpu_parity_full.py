@@ -61,16 +61,29 @@ def test_training_forward_elbo_vs_oracle(name, dev):
           f'KL_y rel {abs(kl_y - ry) / abs(ry):.2e}; KL_z rel {abs(kl_z - rz) / abs(rz):.2e}; per-pixel MSE {mse:.2e}')
     assert nll == pytest.approx(rn, rel=1e-4)
     assert kl_y == pytest.approx(ry, rel=1e-2)
-    # KL(z): 1e-2 -- except at KTH's T = 20, where the untrained dynamics have grown |y| from 4.5 to ~300 over 38 Euler steps and amplify
-    # any perturbation of the encodings alike (the term moves by 0.2 - 2 % between two bf16 runs that differ in summation order)
-    assert kl_z == pytest.approx(rz, rel=1e-2 if name != 'kth_shape' else 5e-2)
+    # KL(z), frame by frame: 1e-2 on every frame whose latent state is still of moderate size (mean |y| < 20 in the reference).
+    # At INITIALISATION the residual dynamics are expansive: at KTH's T = 20 the per-frame KL grows ~30x per frame at the end (9.2 at
+    # t = 1, 2.8e5 at t = 18, 1.0e7 at t = 19 = 97 % of the total) and the deviation grows with it, 1e-3 -> 2e-2 at t = 18; the last
+    # frame alone moved between 1e-3 and 7e-2 when EIGHT of the 12.6 M outputs of the first convolution rounded to the other bf16
+    # neighbour (generic vs im2col kernel, both within one ulp of torch; profiles/r03z_kth_chaos.log). The total of that shape is
+    # therefore held to 1.5e-1 and the per-frame bound carries the parity statement.
+    def klz_frames(q, p):
+        lq, rq = q.chunk(2, -1)
+        lp, rp = p.chunk(2, -1)
+        return O.kl_normal(lq, torch.nn.functional.softplus(rq) + 1e-8, lp, torch.nn.functional.softplus(rp) + 1e-8).sum((1, 2))
+    kf, kr = klz_frames(out[5].cpu(), out[6].cpu()), klz_frames(o['q_z_params'], o['p_z_params'])
+    moderate = o['y'][1:].abs().mean((1, 2)) < 20
+    assert bool(moderate[:8].all())
+    assert float(((kf - kr).abs() / kr.abs())[moderate].max()) < 1e-2
+    kl_tol = 1e-2 if name != 'kth_shape' else 1.5e-1
+    assert kl_z == pytest.approx(rz, rel=kl_tol)
     assert mse < 5e-5
     # Total ELBO: 1e-4 wherever the likelihood term dominates (BAIR, the configuration the metric is quoted on: measured 8e-6; Human,
     # smmnist). At INITIALISATION the residual dynamics grow the state exponentially with the number of Euler steps (|y| doubles every
     # ~3 frames with orthogonal gain 1.2), so at KTH's T = 20 the KL(z) term (tolerance 1e-2, bf16 operands in the latent MLPs) is ~90 %
     # of the total: the total is then held to what the per-term tolerances imply.
     kl_share = (loss_cfg['beta_y'] * abs(ry) + loss_cfg['beta_z'] * abs(rz)) / B / abs(rl)
-    assert loss == pytest.approx(rl, rel=1e-4 + (1e-2 if name != 'kth_shape' else 5e-2) * kl_share)
+    assert loss == pytest.approx(rl, rel=1e-4 + kl_tol * kl_share)
     if name == 'bair_full':
         assert loss == pytest.approx(rl, rel=1e-4)
     for i, n in [(1, 'y'), (2, 'z'), (3, 'w')]:

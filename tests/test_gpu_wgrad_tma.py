@@ -207,3 +207,36 @@ def test_conv3x3_per_video_addend_split(dev, C, H):
     tot = r[1].sum(0)                                    # (C, 2): sum, sumsq of the stored bf16 values
     zs = r[0].float().view(-1, C)
     assert rel(tot[:, 0], zs.sum(0)) < 1e-3 and rel(tot[:, 1], (zs * zs).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize('C,H', [(64, 64), (128, 32), (512, 8)])
+def test_conv3x3_per_video_term_as_hilo_stages(dev, C, H):
+    """The same split with the per-video term fed through the tensor core (engine._decoder_fwd at resolution >= 32): one launch stores
+    conv_s(s) as [hi | lo] bf16, the per-frame launch reads it as a second source (frame -> video map) whose K stages use the centre
+    tap against identity weights. Checks the hi/lo store (hi + lo = fp32 result to 2^-16), the final result vs F.conv2d over the
+    concatenation (tighter than one bf16 rounding of the addend would allow), the statistics, and that a_out holds only h."""
+    from srvp_b200 import ops
+    torch.manual_seed(C + 1)
+    nt, B = 3, 4
+    Fr = nt * B
+    h = (torch.randn(Fr, H, H, C, device=dev) * 0.5).to(torch.bfloat16)
+    sk = (torch.randn(B, H, H, C, device=dev) * 0.5).to(torch.bfloat16)
+    w = torch.randn(C, 2 * C, 3, 3, device=dev) * 0.03
+    wb = w.to(torch.bfloat16).float()
+    ref_s = F.conv2d(sk.float().permute(0, 3, 1, 2), wb[:, C:], padding=1).permute(0, 2, 3, 1)
+    cat = torch.cat([h.float(), sk.float().repeat(nt, 1, 1, 1)], 3).permute(0, 3, 1, 2)
+    ref = F.conv2d(cat, wb, padding=1).permute(0, 2, 3, 1)
+    rs = ops.conv3x3([ops.Src(sk, C)], ops.pack_conv3x3(w, 'conv', cin_range=(C, C)), B, H, H, C, out_hilo=True)
+    assert tuple(rs[0].shape) == (B, H, H, 2 * C)
+    hl = rs[0].float()
+    assert float(((hl[..., :C] + hl[..., C:]) - ref_s).abs().max() / ref_s.abs().max()) < 1e-4
+    vid = torch.arange(B, dtype=torch.int32, device=dev).repeat(nt)
+    wp = ops.concat_packs([ops.pack_conv3x3(w, 'conv', cin_range=(0, C)), ops.hilo_identity_pack(C, dev)], C)
+    masks = [0x1ff] * (C // 64) + [0x010] * (2 * C // 64)
+    r = ops.conv3x3([ops.Src(h, C), ops.Src(rs[0], 2 * C, None, None, vid, 0, 0, False)], wp, Fr, H, H, C, stats=True, save_input=True,
+                    tap_masks=masks, a_out_channels=C, cin_real=C)
+    assert rel(r[0].float(), ref) < 6e-3                 # output rounding only
+    tot = r[1].sum(0)
+    zs = r[0].float().view(-1, C)
+    assert rel(tot[:, 0], zs.sum(0)) < 1e-3 and rel(tot[:, 1], (zs * zs).sum(0)) < 1e-3
+    assert tuple(r[2].shape) == (Fr, H, H, C) and torch.equal(r[2], h)
