@@ -374,26 +374,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mtile = tile / p.num_nblk, nblk = tile % p.num_nblk;
       const int as = tcount % C::ACC_STAGES;
-      if constexpr (EPI == SRVP_EPI_RAW_BF16) {
-        if (p.add != nullptr && (lane & 7) == 0) {
-          // The per-video addend is fetched by the thread that owns the row, batch after batch (8 dependent round trips per 512-row
-          // tile): from HBM each costs ~1 us and the epilogue, not the MMAs, paces the layer (+1.1 ms on the 64-channel 64x64 layer,
-          // profiles/r03k_fwd_ablate.log). Pull the addend of this CTA's NEXT tile into L2 now -- one full epilogue of lead time; 8 lanes
-          // share a 128-byte line of a channel-group plane, so every 8th lane asks for it.
-          const int ntile = tile + gridDim.x;
-          if (ntile < total_tiles) {
-            const int nmt = ntile / p.num_nblk, nnb = ntile % p.num_nblk;
-            const size_t npix = (size_t)p.add_frames * p.H * p.W;
-#pragma unroll 1
-            for (int mb = 0; mb < C::MBLK; ++mb) {
-              const long long v = (long long)nmt * MT + mb * 128 + tid;
-              int f = 0, y = 0, x = 0;
-              if (decode_vpix(v, p.vtotal, HpWp, p.Wp, p.H, p.W, f, y, x)) {
-                const float4* ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nnb * NB) >> 2) * npix + (size_t)(((f % p.add_frames) * p.H + y) * p.W + x);
+      // Per-video addend, software-pipelined: the 8 float4 of a 32-column batch are requested one batch AHEAD -- the first one before the
+      // accumulators are even awaited, the following ones right after the previous batch has been added -- so that their round trip
+      // (HBM: the per-video tensor is re-read once per frame, 12 x 200 MB) runs under the pack / stage / statistics / store work of the
+      // current batch instead of in front of it.
+      // (N blocks of 256 columns keep 16 statistics accumulators per thread and have no registers left for the look-ahead: they fetch
+      // each batch where it is used; their layers are the small images, where the addend costs little.)
+      constexpr bool kPipeAdd = EPI == SRVP_EPI_RAW_BF16 && NB <= 128;
+      [[maybe_unused]] float4 pre[kPipeAdd ? 8 : 1];
+      [[maybe_unused]] const float4* pre_ap = nullptr;
+      [[maybe_unused]] const size_t add_npix = (size_t)p.add_frames * p.H * p.W;
+      if constexpr (kPipeAdd) {
+        if (p.add != nullptr) {
+          int f0 = 0, y0 = 0, x0 = 0;
+          if (decode_vpix((long long)mtile * MT + tid, p.vtotal, HpWp, p.Wp, p.H, p.W, f0, y0, x0)) {
+            pre_ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nblk * NB) >> 2) * add_npix + (size_t)(((f0 % p.add_frames) * p.H + y0) * p.W + x0);
 #pragma unroll
-                for (int q = 0; q < NB / 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)q * npix));
-              }
-            }
+            for (int q = 0; q < 8; ++q) pre[q] = __ldg(pre_ap + (size_t)q * add_npix);
           }
         }
       }
@@ -457,15 +454,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
               // write consecutive 16-byte pieces of one channel-group plane -- coalesced. In the pixel-major (frames, H, W, cout)
               // layout every one of these requests touched 32 different 128-byte lines and the addend cost more than the MMAs of the
               // 64-channel 64x64 layer (+1.06 ms, profiles/r03k_fwd_ablate.log).
-              if (p.add != nullptr && valid) {
-                // per-video term of a convolution split over cat[h, skip]: conv(cat[h, s]) = conv_h(h) + conv_s(s), s constant over time
-                const size_t npix = (size_t)p.add_frames * p.H * p.W;
-                const float4* ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nblk * NB + bi * 32) >> 2) * npix +
-                                   (size_t)(((f % p.add_frames) * p.H + y) * p.W + x);
+              if constexpr (!kPipeAdd) {
+                if (p.add != nullptr && valid) {
+                  const float4* ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nblk * NB + bi * 32) >> 2) * add_npix +
+                                     (size_t)(((f % p.add_frames) * p.H + y) * p.W + x);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 t4 = __ldg(ap + (size_t)q * npix);
-                  vals[4 * q] += t4.x; vals[4 * q + 1] += t4.y; vals[4 * q + 2] += t4.z; vals[4 * q + 3] += t4.w;
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 t4 = __ldg(ap + (size_t)q * add_npix);
+                    vals[4 * q] += t4.x; vals[4 * q + 1] += t4.y; vals[4 * q + 2] += t4.z; vals[4 * q + 3] += t4.w;
+                  }
+                }
+              } else if (p.add != nullptr) {
+                // per-video term of a convolution split over cat[h, skip]: conv(cat[h, s]) = conv_h(h) + conv_s(s), s constant over time
+                if (valid) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    vals[4 * q] += pre[q].x; vals[4 * q + 1] += pre[q].y; vals[4 * q + 2] += pre[q].z; vals[4 * q + 3] += pre[q].w;
+                  }
+                }
+                // request the next batch: the following 32 columns of this row, or the first 32 of this thread's row in the next M block
+                constexpr int NBI = NB / 32;
+                if (bi + 1 < NBI) {
+                  if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pre[q] = __ldg(pre_ap + (size_t)((bi + 1) * 8 + q) * add_npix);
+                  }
+                } else if (mb + 1 < C::MBLK) {
+                  int f1 = 0, y1 = 0, x1 = 0;
+                  if (decode_vpix(v + 128, p.vtotal, HpWp, p.Wp, p.H, p.W, f1, y1, x1)) {
+                    pre_ap = reinterpret_cast<const float4*>(p.add) + (size_t)((nblk * NB) >> 2) * add_npix + (size_t)(((f1 % p.add_frames) * p.H + y1) * p.W + x1);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pre[q] = __ldg(pre_ap + (size_t)q * add_npix);
+                  }
                 }
               }
               if (p.out_raw_f32 != nullptr && valid) {
