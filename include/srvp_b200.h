@@ -104,6 +104,18 @@ int srvp_conv3x3(const srvp_conv3x3_args* args, void* stream);
  * conv fwd: (Cin*9, 9, 0); conv dgrad: (9, Cin*9, 1); convT fwd: (9, Cout*9, 1); convT dgrad: (Cout*9, 9, 0). */
 int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32_t n_real, int32_t n_padded, int32_t k_real,
                               int32_t k_padded, int64_t stride_n, int64_t stride_k, int32_t flip, void* stream);
+/* The same for every 3x3 weight of a model in ONE launch (the weights change once per optimizer step; 46 separate launches sat between
+ * the convolutions of the critical path). jobs_dev: DEVICE table sorted by block_start; job i is packed by the 256-thread blocks
+ * [block_start_i, block_start_i + ceil(n_padded*k_padded*9/8 / 256)); nb / kch = N block (srvp_conv3x3_nblock) and 8-channel chunks
+ * per K stage (2 for k_padded == 16, else 8) of the consuming kernel variant. */
+typedef struct {
+  const float* w;
+  srvp_bf16* wpack;
+  int64_t stride_n, stride_k;
+  int32_t n_real, n_padded, k_real, k_padded;
+  int32_t flip, nb, kch, block_start;
+} srvp_pack_job;
+int srvp_pack_conv3x3_multi(const srvp_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 4x4 / stride 2 / pad 1 convolutions of the DCGAN64 encoder/decoder (module/conv.py:173-179 nn.Conv2d(.,.,4,2,1),

@@ -33,6 +33,11 @@ class Conv3x3Args(ctypes.Structure):
                 ('add_f32', c_ptr), ('add_frames', c_int), ('out_raw_f32', c_ptr), ('out_hilo', c_int), ('a_out_channels', c_int)]
 
 
+class PackJob(ctypes.Structure):
+    _fields_ = [('w', c_ptr), ('wpack', c_ptr), ('stride_n', c_i64), ('stride_k', c_i64), ('n_real', c_int), ('n_padded', c_int), ('k_real', c_int),
+                ('k_padded', c_int), ('flip', c_int), ('nb', c_int), ('kch', c_int), ('block_start', c_int)]
+
+
 class Wgrad3x3Args(ctypes.Structure):
     _fields_ = [('act', c_ptr), ('act_channels', c_int), ('act_cpitch', c_int), ('act_coff', c_int), ('dz', c_ptr),
                 ('dz_channels', c_int), ('dz_cpitch', c_int), ('dz_coff', c_int), ('frames', c_int), ('H', c_int), ('W', c_int), ('cout', c_int), ('cin', c_int),
@@ -110,7 +115,7 @@ def lib():
 # every symbol declared in include/srvp_b200.h
 EXPORTS = [
     'srvp_last_error', 'srvp_version', 'srvp_num_sms', 'srvp_launch_count', 'srvp_conv3x3_num_mtiles', 'srvp_conv3x3_nblock', 'srvp_conv3x3',
-    'srvp_pack_conv3x3_weights', 'srvp_pack_conv4x4s2_weights', 'srvp_conv4x4s2_tap_mask', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16',
+    'srvp_pack_conv3x3_weights', 'srvp_pack_conv3x3_multi', 'srvp_pack_conv4x4s2_weights', 'srvp_conv4x4s2_tap_mask', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16',
     'srvp_nchw_f32_to_s2d_bf16', 'srvp_sigmoid_bwd_nchw_to_s2d16', 'srvp_nhwc_bf16_to_nchw_f32',
     'srvp_materialize_src', 'srvp_sum_over_time_bf16', 'srvp_sum_slices_f32', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
     'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',

@@ -607,6 +607,39 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
   reinterpret_cast<uint4*>(wpack)[idx] = o;
 }
 
+// All the 3x3 weight operands of a model in ONE launch: block b works on the job whose [block_start, next block_start) range holds b
+// (binary search over the device table), then exactly like pack_conv3x3_kernel.
+__global__ void pack_conv3x3_multi_kernel(const srvp_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const srvp_pack_job j = jobs[lo];
+  const long long total = (long long)j.n_padded * j.k_padded * 9 / 8;
+  const long long idx = (long long)(blockIdx.x - j.block_start) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long t = idx;
+  const int n = (int)(t % j.nb); t /= j.nb;
+  const int jj = (int)(t % j.kch); t /= j.kch;
+  const int tap = (int)(t % 9); t /= 9;
+  const int nstages = j.k_padded / (j.kch * 8);
+  const int stage = (int)(t % nstages); t /= nstages;
+  const int nblk = (int)t;
+  const int ng = nblk * j.nb + n;
+  const int k0 = (stage * j.kch + jj) * 8;
+  const int te = j.flip ? 8 - tap : tap;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    v[e] = (ng < j.n_real && k < j.k_real) ? j.w[(long long)ng * j.stride_n + (long long)k * j.stride_k + te] : 0.f;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(j.wpack)[idx] = o;
+}
+
 // 4x4 / stride 2 / pad 1 weights packed for the same kernel (see include/srvp_b200.h): every (phase, 3x3 tap) pair is one of
 // the 16 taps of the 4x4 kernel or zero. DOWN: ky = 2*ty + py - 1 (phase from k); UP_*: ky = py + 3 - 2*ty (phase from n / fixed).
 __global__ void pack_conv4x4s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpack, int kind, int chan_n, int n_padded,
@@ -832,6 +865,13 @@ extern "C" int srvp_pack_conv3x3_weights(const float* w, srvp_bf16* wpack, int32
   pack_conv3x3_kernel<<<(unsigned)blocks, threads, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wpack), n_real, n_padded, k_real, k_padded,
                                                                 stride_n, stride_k, flip, ch.NB, KCH);
   return check_launch("pack_conv3x3");
+}
+
+extern "C" int srvp_pack_conv3x3_multi(const srvp_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRVP_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_blocks > 0, "pack_multi: empty job table");
+  pack_conv3x3_multi_kernel<<<(unsigned)total_blocks, 256, 0, stream>>>(jobs_dev, njobs);
+  return check_launch("pack_conv3x3_multi");
 }
 
 extern "C" int srvp_pack_conv4x4s2_weights(const float* w, srvp_bf16* wpack, int32_t kind, int32_t chan_n, int32_t n_padded, int32_t chan_k,

@@ -130,6 +130,8 @@ def _encoder_fwd(enc, x, training, want_stats_update=True):
     plan = _ensure_plan(enc)
     F_ = x.shape[0]
     dev = x.device
+    if training:
+        ops.PACK_EPOCH[0] += 1     # a training forward re-packs the weight operands (one launch), whoever updated the parameters
     c = _EncCtx()
     c.F = F_
     if plan == 'dcgan':
@@ -293,6 +295,8 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
     plan = _ensure_plan(dec)
     assert sigmoid, 'srvp_b200: decoder without the final sigmoid is not built'
     F_, dev = dec_inp.shape[0], dec_inp.device
+    if training:
+        ops.PACK_EPOCH[0] += 1     # see _encoder_fwd
     c = _DecCtx()
     c.F, c.dec_inp = F_, dec_inp
     up_conv, up_bn = _first_block(dec)

@@ -2,6 +2,7 @@
 import contextlib
 import ctypes
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -130,30 +131,106 @@ def padded_k(k):
     return 16 if k <= 16 else pad_to(k, 64)
 
 
-@profiled('pack_conv3x3')
-def pack_conv3x3(weight, kind, out=None, cin_range=None):
-    """fp32 (.,.,3,3) weight -> packed bf16 B operand. cin_range = (first, count) packs only those INPUT channels of an nn.Conv2d
-    weight ('conv': they are the K dimension; 'conv_dgrad': the N dimension) -- the two halves of a convolution over cat[h, skip]."""
-    assert weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
+# ------------------------------------------------------------------------------------------------ packed weights
+# The packed bf16 operands are functions of the weights only, and the weights change once per optimizer step: pack_conv3x3() keeps one
+# persistent buffer per (weight storage, kind, input-channel range) and re-packs ALL registered operands in ONE launch
+# (srvp_pack_conv3x3_multi) the first time a stale one is asked for -- forward and data-gradient operands alike, so no pack launch is
+# left between the convolutions of the critical path (it was 46 launches per step), and evaluation loops never re-pack at all.
+# Freshness: the tensor's in-place version counter (torch optimizers, load_state_dict, init) AND PACK_EPOCH, which srvp_b200.optim.Adam
+# bumps because its kernel updates the parameters through raw pointers.
+PACK_CACHE = int(os.environ.get('SRVP_PACK_CACHE', '1'))
+PACK_EPOCH = [0]
+_PACKS = {}          # key -> _PackEntry
+_PACK_TABLE = {}     # device index -> (device job table, njobs, total blocks, entries) or None when the registry changed
+
+
+class _PackEntry:
+    __slots__ = ('wref', 'ptr0', 'out', 'job', 'version', 'epoch', 'device')
+
+
+def _pack_job(weight, kind, cin_range):
     if kind in ('conv', 'conv_dgrad'):
         cout, cin = weight.shape[0], weight.shape[1]
     else:
         cin, cout = weight.shape[0], weight.shape[1]
     n_real, k_real, sn, sk, flip = conv3x3_kind_strides(kind, cout, cin)
-    wptr = ptr(weight)
+    wptr = weight.data_ptr()
     if cin_range is not None:
         assert kind in ('conv', 'conv_dgrad')
         c0, cn = cin_range
-        wptr = ctypes.c_void_p(weight.data_ptr() + 4 * c0 * 9)
+        wptr += 4 * c0 * 9
         if kind == 'conv':
             k_real = cn
         else:
             n_real = cn
-    n_pad, k_pad = padded_n(n_real), padded_k(k_real)
+    return wptr, n_real, padded_n(n_real), k_real, padded_k(k_real), sn, sk, flip
+
+
+def _refresh_packs(device):
+    """Re-pack every registered operand of `device` whose weight is still alive (one launch) and mark them fresh."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    tab = _PACK_TABLE.get(idx)
+    if tab is not None:
+        for e in tab[3]:          # the table holds raw pointers: every weight must still be alive at its recorded address
+            w = e.wref()
+            if w is None or w.data_ptr() != e.ptr0:
+                tab = None
+                break
+    if tab is None:
+        entries = []
+        for key in list(_PACKS):
+            e = _PACKS[key]
+            w = e.wref()
+            if w is None or w.data_ptr() != e.ptr0:       # parameter gone or re-allocated: forget the operand
+                del _PACKS[key]
+            elif e.device == idx:
+                entries.append(e)
+        jobs = (_lib.PackJob * len(entries))()
+        start = 0
+        for i, e in enumerate(entries):
+            wptr, n_real, n_pad, k_real, k_pad, sn, sk, flip = e.job
+            jb = jobs[i]
+            jb.w, jb.wpack, jb.stride_n, jb.stride_k = wptr, e.out.data_ptr(), sn, sk
+            jb.n_real, jb.n_padded, jb.k_real, jb.k_padded, jb.flip = n_real, n_pad, k_real, k_pad, flip
+            jb.nb, jb.kch, jb.block_start = lib().srvp_conv3x3_nblock(c_int(n_pad)), (2 if k_pad == 16 else 8), start
+            start += (n_pad * k_pad * 9 // 8 + 255) // 256
+        raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).clone()
+        tab = _PACK_TABLE[idx] = (raw.to(device), len(entries), start, entries)
+    dev_tab, njobs, blocks, entries = tab
+    if njobs:
+        check(lib().srvp_pack_conv3x3_multi(ptr(dev_tab), c_int(njobs), c_int(blocks), stream_ptr()), 'pack_conv3x3_multi')
+    for e in entries:
+        w = e.wref()
+        if w is not None:
+            e.version, e.epoch = w._version, PACK_EPOCH[0]
+
+
+@profiled('pack_conv3x3')
+def pack_conv3x3(weight, kind, out=None, cin_range=None):
+    """fp32 (.,.,3,3) weight -> packed bf16 B operand. cin_range = (first, count) packs only those INPUT channels of an nn.Conv2d
+    weight ('conv': they are the K dimension; 'conv_dgrad': the N dimension) -- the two halves of a convolution over cat[h, skip].
+    Without `out` the result is a cached, persistent buffer (see above): do not write to it."""
+    assert weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
+    job = _pack_job(weight, kind, cin_range)
+    wptr, n_real, n_pad, k_real, k_pad, sn, sk, flip = job
+    cached = out is None and PACK_CACHE and not torch.cuda.is_current_stream_capturing()
+    if cached:
+        key = (weight.data_ptr(), kind, cin_range, tuple(weight.shape), weight.device.index)
+        e = _PACKS.get(key)
+        if e is not None and e.wref() is weight:
+            if e.version != weight._version or e.epoch != PACK_EPOCH[0]:
+                _refresh_packs(weight.device)
+            return e.out
     if out is None:
         out = torch.empty(n_pad * k_pad * 9, dtype=torch.bfloat16, device=weight.device)
-    check(lib().srvp_pack_conv3x3_weights(wptr, ptr(out), c_int(n_real), c_int(n_pad), c_int(k_real), c_int(k_pad),
+    check(lib().srvp_pack_conv3x3_weights(ctypes.c_void_p(wptr), ptr(out), c_int(n_real), c_int(n_pad), c_int(k_real), c_int(k_pad),
                                          c_i64(sn), c_i64(sk), c_int(flip), stream_ptr()), 'pack_conv3x3_weights')
+    if cached:
+        e = _PackEntry()
+        e.wref, e.ptr0, e.out, e.job = weakref.ref(weight), weight.data_ptr(), out, job
+        e.version, e.epoch, e.device = weight._version, PACK_EPOCH[0], weight.device.index
+        _PACKS[key] = e
+        _PACK_TABLE[e.device] = None          # the job table is rebuilt at the next refresh
     return out
 
 

@@ -75,4 +75,5 @@ class Adam(torch.optim.Optimizer):
             check(lib().srvp_adam_multi(_lib.c_ptr(table.data_ptr()), _lib.c_ptr(sizes.data_ptr()), _lib.c_ptr(starts.data_ptr()), c_int(len(params)),
                                        c_int(nblocks), _lib.ctypes.c_double(group['lr']), _lib.ctypes.c_double(b1), _lib.ctypes.c_double(b2),
                                        _lib.ctypes.c_double(group['eps']), c_i64(step), stream_ptr()), 'adam_multi')
+        ops.PACK_EPOCH[0] += 1      # the parameters changed through raw pointers: cached packed operands (ops.pack_conv3x3) are stale
         return loss

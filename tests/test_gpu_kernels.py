@@ -515,3 +515,37 @@ def test_thin_wgrad_both_ends(dev, nc, frames):
     dwt2 = torch.zeros(64, nc, 3, 3, device=dev)
     ops.wgrad3x3(a.to(torch.bfloat16), 64, dzt, 16, frames, 64, 64, nc, 64, dwt2, 'convT')
     assert rel(dwt2, wt.grad) < 2e-3
+
+
+def test_packed_weight_cache_follows_the_weights(dev):
+    """ops.pack_conv3x3 returns a cached operand; it must follow in-place updates of the weight (version counter), updates through raw
+    pointers by srvp_b200.optim.Adam (PACK_EPOCH) and training-mode forwards, and re-pack every registered operand in one launch."""
+    from srvp_b200 import ops, _lib
+    from srvp_b200.optim import Adam
+    w1 = torch.nn.Parameter(torch.randn(64, 64, 3, 3, device=dev) * 0.1)
+    w2 = torch.nn.Parameter(torch.randn(128, 64, 3, 3, device=dev) * 0.1)
+    fresh = lambda w, kind: ops.pack_conv3x3(w.detach().clone(), kind, out=torch.empty(ops.padded_n(w.shape[0] if kind == 'conv' else w.shape[1]) *
+                                                                                   ops.padded_k(w.shape[1] if kind == 'conv' else w.shape[0]) * 9,
+                                                                                   dtype=torch.bfloat16, device=dev))
+    a1, a2, a3 = ops.pack_conv3x3(w1, 'conv'), ops.pack_conv3x3(w2, 'conv'), ops.pack_conv3x3(w2, 'conv_dgrad')
+    assert ops.pack_conv3x3(w1, 'conv') is a1                      # cache hit: same buffer, no launch
+    n0 = _lib.lib().srvp_launch_count()
+    ops.pack_conv3x3(w1, 'conv'); ops.pack_conv3x3(w2, 'conv_dgrad')
+    assert _lib.lib().srvp_launch_count() == n0
+    with torch.no_grad():
+        w1.mul_(2.0)                                               # in-place update: version counter
+        w2.add_(0.5)
+    n0 = _lib.lib().srvp_launch_count()
+    b1 = ops.pack_conv3x3(w1, 'conv')
+    assert _lib.lib().srvp_launch_count() == n0 + 1                # ONE launch refreshed all three operands
+    assert b1 is a1 and torch.equal(b1, fresh(w1, 'conv'))
+    assert torch.equal(ops.pack_conv3x3(w2, 'conv'), fresh(w2, 'conv')) and torch.equal(ops.pack_conv3x3(w2, 'conv_dgrad'), fresh(w2, 'conv_dgrad'))
+    assert _lib.lib().srvp_launch_count() == n0 + 1 + 3            # (the three `fresh` packs themselves)
+    opt = Adam([w1, w2], lr=1e-2)
+    w1.grad, w2.grad = torch.ones_like(w1), torch.ones_like(w2)
+    opt.step()                                                     # raw-pointer update: PACK_EPOCH
+    assert torch.equal(ops.pack_conv3x3(w1, 'conv'), fresh(w1, 'conv')) and torch.equal(ops.pack_conv3x3(w2, 'conv_dgrad'), fresh(w2, 'conv_dgrad'))
+    del w2                                                         # a dead weight drops out of the job table at the next refresh
+    with torch.no_grad():
+        w1.mul_(0.5)
+    assert torch.equal(ops.pack_conv3x3(w1, 'conv'), fresh(w1, 'conv'))
