@@ -181,6 +181,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
       const bool store_tile = p.a_out != nullptr && (tile % p.num_nblk) == 0;
       for (int s = 0; s < p.nstages; ++s, ++it) {
         const bool store_a = store_tile && s < p.a_out_stages;
+        if (p.dbg & 32) {       // development: no loader work at all, only the halo hand-off
+          mbar_wait(&halo_empty[it % kHaloStages], ((it / kHaloStages) & 1) ^ 1);
+          mbar_arrive(&halo_full[it % kHaloStages]);
+          continue;
+        }
         const int hs = it % kHaloStages;
         const bool second = s >= p.stages0;
         const SrcDev& sd = p.src[second ? 1 : 0];
@@ -358,8 +363,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
             if (TPS == 1 && !((tmask >> q) & 1u)) continue;
             mbar_wait(&w_empty[ws], wph ^ 1u);
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
-              bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
+              if (p.dbg & 16) {   // development: no weight transfers, only the ring hand-off
+                mbar_arrive(&w_full[ws]);
+              } else {
+                mbar_arrive_expect_tx(&w_full[ws], C::SLOT_BYTES);
+                bulk_g2s(wslots + (size_t)ws * C::SLOT_BYTES, wsrc + ((size_t)s * 9 + q * TPS) * KCH * NB * 16, C::SLOT_BYTES, &w_full[ws]);
+              }
             }
             if (++ws == WS) { ws = 0; wph ^= 1u; }
           }
@@ -403,6 +412,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
       for (int i = 0; i < NBAT; ++i) s1[i] = s2[i] = 0.f;
       const bool do_stats = p.stats_partial != nullptr;
 
+      if (p.dbg & 8) {          // development: no epilogue work at all, only the accumulator hand-off
+        tc_fence_before();
+        mbar_arrive(&acc_empty[as]);
+        continue;
+      }
 #pragma unroll 1
       for (int mb = 0; mb < C::MBLK; ++mb) {
         const long long v = (long long)mtile * MT + mb * 128 + tid;
