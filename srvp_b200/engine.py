@@ -455,10 +455,9 @@ def _decoder_head_bwd(dec, c, da, da_mode, grads, direct):
     else:
         head_wgrad()
     # The decoder's weight gradients may keep running under the latent / inference-network backward (few-CTA, latency-bound kernels)
-    # when every gradient lives in the GradBucket (consumed only after allreduce_mean() / Adam.step(), which join) and no early
-    # all-reduce of the decoder segment is about to read them; otherwise they must be final here.
-    from . import parallel
-    if all(direct) and ops.DEFER_JOIN and parallel.world() == 1:
+    # when every gradient lives in the GradBucket (consumed only after allreduce_mean() / Adam.step(), which join; the early all-reduce
+    # of the decoder segment is issued behind the weight-gradient stream, DecoderFn.backward); otherwise they must be final here.
+    if all(direct) and ops.DEFER_JOIN:
         ops.flush_wgrads(held=True)
     else:
         ops.join_wgrads()
@@ -481,8 +480,10 @@ class DecoderFn(torch.autograd.Function):
         ops.PROFILE_TAG = ''
         ctx.c = None
         from . import parallel
-        if parallel.ACTIVE_BUCKET is not None:
-            parallel.ACTIVE_BUCKET.segment_ready()     # the decoder's gradients are final: their all-reduce overlaps the rest of backward
+        if parallel.ACTIVE_BUCKET is not None and parallel.world() > 1:
+            # the decoder's gradients are complete once the weight-gradient stream has drained: their all-reduce is issued behind that
+            # stream and overlaps the rest of the backward pass without holding the main stream back
+            ops.after_side(parallel.ACTIVE_BUCKET.segment_ready)
         return (None, d_inp, None, None, None, None, *grads)
 
 

@@ -375,6 +375,22 @@ def side_section(*keep):
     _SIDE_BUSY[0] = True
 
 
+def after_side(fn):
+    """fn() with the weight-gradient stream current, behind everything enqueued so far on both streams: for work that consumes the
+    weight gradients without involving the main stream (the early all-reduce of the decoder's gradient segment: NCCL orders itself
+    behind the stream that is current when the collective is called)."""
+    if not (WGRAD_STREAM and PROFILE is None):
+        join_wgrads()
+        return fn()
+    flush_wgrads(held=True)
+    side = _side_stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        r = fn()
+    _SIDE_BUSY[0] = True
+    return r
+
+
 def join_wgrads():
     """The current stream waits for every weight-gradient launch recorded so far."""
     flush_wgrads(held=True)
