@@ -174,11 +174,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
   if (warp >= 4 && warp < kMmaWarp) {
     // ------------------------------------------------------------------ activation loaders
     const int lt = tid - 128;
+    constexpr int RSTEP = kLoaders / KCH;         // rows between two rows of the same thread
+    const int r0 = lt / KCH;
+    const int adv_f = RSTEP / HpWp, adv_y = (RSTEP % HpWp) / p.Wp, adv_x = (RSTEP % HpWp) % p.Wp;
     uint32_t it = 0;  // halo stage iteration counter
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mtile = tile / p.num_nblk;
       const long long vbase = (long long)mtile * MT - p.Wp - 1;
       const bool store_tile = p.a_out != nullptr && (tile % p.num_nblk) == 0;
+      VRow row0;                                  // this thread's first row of the tile (the same for every K stage)
+      vrow_init(row0, vbase + r0, HpWp, p.Wp);
       for (int s = 0; s < p.nstages; ++s, ++it) {
         const bool store_a = store_tile && s < p.a_out_stages;
         if (p.dbg & 32) {       // development: no loader work at all, only the halo hand-off
@@ -198,26 +203,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           // row read / write 16*KCH contiguous bytes of global memory (coalesced source reads and a_out stores), and the chunk's BN
           // scale / shift live in registers for the whole stage. Phase 1 issues all copies (cp.async straight into the halo tile,
           // zero-filled for pad pixels), phase 2 walks the same rows again and applies BN + LeakyReLU in place.
-          constexpr int RSTEP = kLoaders / KCH;
-          const int j = lt % KCH, r0 = lt / KCH;
-          const int rp = sd.row_pitch ? sd.row_pitch : p.W;
-          VRow row0;
-          vrow_init(row0, vbase + r0, HpWp, p.Wp);
-          const int adv_f = RSTEP / HpWp, adv_y = (RSTEP % HpWp) / p.Wp, adv_x = (RSTEP % HpWp) % p.Wp;
+          // The row walk is the loader's critical resource: with ~110 instructions per row (64-bit index products, the source
+          // description re-read from the parameter bank with a dynamic index, a generic -> shared conversion per copy) the loader
+          // warps needed 2.5 us per stage with every copy DISABLED (profiles/r04e_conv_dbg_ablation.log). Everything that does not change
+          // from row to row is therefore taken out of the loop, pixel indices are 32-bit (the host checks the range) and the nearest-
+          // upsample is a shift.
+          const int j = lt % KCH;
+          const int sh = (sd.mode == SRVP_SRC_UP2) ? 1 : 0;
+          const int Hs = p.H >> sh;
+          const int Ws = (sd.row_pitch ? sd.row_pitch : p.W) >> sh;
+          const int scp = sd.cpitch;
+          const int* fmap = sd.frame_map;
+          const __nv_bfloat16* sbase = sd.ptr + sd.coff + cloc + j * 8;
+          const uint32_t dplane = smem_u32(hbuf) + (uint32_t)(j * P) * 16u;
+          const bool nocopy = (p.dbg & 1) != 0;
           uint32_t vmask = 0;   // validity of this thread's rows (P / RSTEP <= 32 rows, checked on the host)
           {
             VRow rw = row0;
             int i = 0;
+#pragma unroll 1
             for (int r = r0; r < P; r += RSTEP, ++i) {
-              const bool valid = rw.f >= 0 && rw.f < p.F && rw.y < p.H && rw.x < p.W;
-              const __nv_bfloat16* src = sd.ptr;
-              if (valid) {
-                const int fs = sd.frame_map ? __ldg(sd.frame_map + rw.f) : rw.f;
-                if (sd.mode == SRVP_SRC_UP2) src = sd.ptr + (((size_t)fs * (p.H >> 1) + (rw.y >> 1)) * (p.W >> 1) + (rw.x >> 1)) * sd.cpitch + sd.coff + cloc + j * 8;
-                else src = sd.ptr + (((size_t)fs * p.H + rw.y) * rp + rw.x) * sd.cpitch + sd.coff + cloc + j * 8;
-                vmask |= 1u << i;
-              }
-              if (!(p.dbg & 1)) cp_async16(hbuf + ((size_t)j * P + r) * 16, src, valid ? 16u : 0u);
+              const bool valid = (unsigned)rw.f < (unsigned)p.F && rw.y < p.H && rw.x < p.W;
+              int fs = rw.f;
+              if (fmap != nullptr && valid) fs = __ldg(fmap + rw.f);
+              const int pix = (fs * Hs + (rw.y >> sh)) * Ws + (rw.x >> sh);
+              const __nv_bfloat16* src = valid ? sbase + (size_t)(unsigned)pix * (unsigned)scp : sbase;
+              vmask |= (valid ? 1u : 0u) << i;
+              if (!nocopy) cp_async16_s(dplane + (uint32_t)r * 16u, src, valid ? 16u : 0u);
               vrow_advance(rw, adv_f, adv_y, adv_x, p.Hp, p.Wp);
             }
           }
@@ -225,16 +237,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
           const bool has_affine = sd.scale != nullptr;
           if (has_affine || sd.lrelu || store_a) {
             const Affine8 af = load_affine8(has_affine ? sd.scale + cloc + j * 8 : nullptr, has_affine ? sd.shift + cloc + j * 8 : nullptr);
+            const int lrelu_on = sd.lrelu;
+            const bool rewrite = has_affine || lrelu_on;
+            uint8_t* plane = hbuf + (size_t)j * P * 16;
+            __nv_bfloat16* abase = store_a ? p.a_out + s * KCH * 8 + j * 8 : nullptr;
+            const int acp = p.a_out_cpitch;
+            const int a_lo = p.Wp + 1, a_hi = p.Wp + 1 + MT;
             VRow rw = row0;
             int i = 0;
 #pragma unroll 4
             for (int r = r0; r < P; r += RSTEP, ++i) {
               if ((vmask >> i) & 1u) {   // pad rows stay zero
-                uint4* slot = reinterpret_cast<uint4*>(hbuf + ((size_t)j * P + r) * 16);
-                const uint4 a = transform8r(*slot, af, sd.lrelu);
-                if (has_affine || sd.lrelu) *slot = a;
-                if (store_a && r >= p.Wp + 1 && r < p.Wp + 1 + MT)
-                  *reinterpret_cast<uint4*>(p.a_out + (size_t)((rw.f * p.H + rw.y) * p.W + rw.x) * p.a_out_cpitch + s * KCH * 8 + j * 8) = a;
+                uint4* slot = reinterpret_cast<uint4*>(plane + (size_t)r * 16);
+                const uint4 a = transform8r(*slot, af, lrelu_on);
+                if (rewrite) *slot = a;
+                if (store_a && r >= a_lo && r < a_hi) {
+                  const int opix = (rw.f * p.H + rw.y) * p.W + rw.x;
+                  *reinterpret_cast<uint4*>(abase + (size_t)(unsigned)opix * (unsigned)acp) = a;
+                }
               }
               vrow_advance(rw, adv_f, adv_y, adv_x, p.Hp, p.Wp);
             }
@@ -242,14 +262,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const ConvDev p) {
         } else {
           // 2x2 max-pooled source, same chunk-owner mapping: four raw loads per output chunk (two rows in flight per thread), ONE
           // transform (pool_transform8r: per-channel min/max then BN + LeakyReLU), constants in registers for the whole stage
-          constexpr int RSTEP = kLoaders / KCH;
           constexpr int UR = 2;
-          const int j = lt % KCH, r0 = lt / KCH;
+          const int j = lt % KCH;
           const int Ws = p.W * 2;
           const Affine8 af = load_affine8(sd.scale ? sd.scale + cloc + j * 8 : nullptr, sd.scale ? sd.shift + cloc + j * 8 : nullptr);
-          VRow rw;
-          vrow_init(rw, vbase + r0, HpWp, p.Wp);
-          const int adv_f = RSTEP / HpWp, adv_y = (RSTEP % HpWp) / p.Wp, adv_x = (RSTEP % HpWp) % p.Wp;
+          VRow rw = row0;
           for (int rb = r0; rb < P; rb += UR * RSTEP) {
             uint4 raw[UR][4];
             int pix[UR];
