@@ -189,9 +189,24 @@ def run_ours(args):
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(xdev)
+    # the caching allocator must have reached its steady state before anything is timed: a step that still grows the pool calls
+    # cudaMalloc (a device synchronisation) in the middle of the pipeline. Extra untimed steps until two consecutive ones leave the
+    # reserved size and the cudaMalloc count unchanged (at most 8).
+    def pool_state():
+        st = torch.cuda.memory_stats(dev)
+        return (st.get('reserved_bytes.all.current', 0), st.get('num_device_alloc', st.get('segment.all.allocated', 0)), st.get('num_alloc_retries', 0))
+    extra_warmup, stable, prev = 0, 0, pool_state()
+    while stable < 2 and extra_warmup < 8:
+        step(xdev)
+        torch.cuda.synchronize()
+        cur = pool_state()
+        stable = stable + 1 if cur == prev else 0
+        prev = cur
+        extra_warmup += 1
     barrier()
     sampler.recording = True
     launches0 = _lib.lib().srvp_launch_count()
+    side0 = ops.SIDE_LAUNCHES[0]
     ms, _ = timed(xdev, args.steps)
     launches = _lib.lib().srvp_launch_count() - launches0
     ms_e2e, lv = timed(xdev, args.steps, hosts=host)
@@ -278,12 +293,20 @@ def run_ours(args):
                             global_batch=batch * world, per_gpu_batch=batch, seq_len=SEQ_LEN,
                             parallelism=f'dp{world}' + (' + SyncBN statistics, one flat gradient all-reduce' if world > 1 else ''),
                             l2='inputs larger than L2: 113 MB batch, >10 GB of activations per step',
+                            extra_warmup_steps=extra_warmup,   # untimed steps after the W warm-up steps until the caching allocator stopped growing
                             e2e_input='uint8 frames (B,T,H,W,C) from pinned host memory, converted on the device',
                             parity='ELBO within 1e-4 rel of the fp32 reference at this size (tests/test_gpu_parity_full.py); KL(z) term within 1e-2'),
                 e2e=dict(value=round(frames * args.steps / (ms_e2e * 1e-3), 1), unit='frames/s', h2d_bytes_per_step=host[0].numel(),
                          d2h_bytes_per_step=4),
                 gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline, conv_stages=stages, hbm_kernels=hbm,
-                kernel_breakdown=breakdown, loss=lv)
+                kernel_breakdown=breakdown,
+                streams=dict(weight_gradient_stream=bool(ops.WGRAD_STREAM), side_launches_per_step=(ops.SIDE_LAUNCHES[0] - side0) // max(1, args.steps * 2),
+                             sum_kernel_ms_serialised=round(tot_ms / 2, 3),
+                             note='timed steps: weight gradients (and, under the GradBucket, the head / latent weight-gradient GEMMs) run on a second '
+                                  'stream next to the HBM-bound batch-norm backward and the few-CTA latent / inference backward kernels '
+                                  '(srvp_b200/ops.py); roofline / conv_stages / hbm_kernels / kernel_breakdown come from 2 extra steps with '
+                                  'everything on one stream and CUDA events around every launch, so their sum exceeds ms_per_step'),
+                loss=lv)
     if other is not None:
         line[other['scaling'] + '_scaling'] = other
     if eager is not None:

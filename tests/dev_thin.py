@@ -33,11 +33,13 @@ wpf = ops.pack_conv3x3(wf, 'convT')
 src = ops.Src(z, 64, sc, sh, None, 0, 0, True)
 print(tag, 'head 64->3 sigmoid + a_out   ', round(timeit(lambda: ops.conv3x3([src], wpf, F_, 64, 64, 3, sigmoid_nchw=True, save_input=True)), 3), 'ms', flush=True)
 print(tag, 'head 64->3 sigmoid, no a_out ', round(timeit(lambda: ops.conv3x3([src], wpf, F_, 64, 64, 3, sigmoid_nchw=True, save_input=False)), 3), 'ms', flush=True)
+print(tag, 'decoder head kernel, no a_out', round(timeit(lambda: ops.decoder_head_fwd(src, wf, F_, 3, save_input=False)), 3), 'ms', flush=True)
 dz16 = torch.randn(F_, 64, 64, 16, device=dev).to(torch.bfloat16)
 wpd = ops.pack_conv3x3(wf, 'convT_dgrad')
 print(tag, 'head dgrad 16->64            ', round(timeit(lambda: ops.conv3x3([ops.Src(dz16, 16)], wpd, F_, 64, 64, 64, cin_real=3)), 3), 'ms', flush=True)
 dwf = torch.zeros_like(wf)
 print(tag, 'head wgrad act64 x dz16      ', round(timeit(lambda: ops.wgrad3x3(z, 64, dz16, 16, F_, 64, 64, 3, 64, dwf, 'convT')), 3), 'ms', flush=True)
+print(tag, 'head wgrad raw z + affine    ', round(timeit(lambda: ops.wgrad3x3(z, 64, dz16, 16, F_, 64, 64, 3, 64, dwf, 'convT', act_affine=(sc, sh, True))), 3), 'ms', flush=True)
 dz64 = torch.randn(F_, 64, 64, 64, device=dev).to(torch.bfloat16)
 dw0 = torch.zeros_like(w0)
 print(tag, 'first wgrad act16 x dz64     ', round(timeit(lambda: ops.wgrad3x3(x16, 16, dz64, 64, F_, 64, 64, 64, 3, dw0, 'conv')), 3), 'ms', flush=True)

@@ -8,6 +8,10 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; 
 timeout 600 python bench.py > gpurun_out/${tag}_bench.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/${tag}_bench.log | cut -c1-1500
 timeout 300 python bench.py --workload smmnist --no-cpu-baseline > gpurun_out/${tag}_bench_smmnist.log 2>&1; echo "bench smmnist rc=$?"; tail -1 gpurun_out/${tag}_bench_smmnist.log | cut -c1-600
 timeout 300 python bench.py --impl reference --steps 2 > gpurun_out/${tag}_bench_reference.log 2>&1; echo "bench reference rc=$?"; tail -1 gpurun_out/${tag}_bench_reference.log | cut -c1-600
+timeout 300 python bench.py --workload human_rollout > gpurun_out/${tag}_bench_rollout.log 2>&1; echo "bench rollout rc=$?"; tail -1 gpurun_out/${tag}_bench_rollout.log | cut -c1-600
+timeout 200 python tools/step_timeline.py > gpurun_out/${tag}_timeline.log 2>&1; echo "timeline rc=$?"; head -1 gpurun_out/${tag}_timeline.log
+timeout 200 python tools/step_profile.py --top 70 > gpurun_out/${tag}_step_profile.log 2>&1; echo "step profile rc=$?"; head -1 gpurun_out/${tag}_step_profile.log
+timeout 200 python tests/dev_thin.py > gpurun_out/${tag}_thin.log 2>&1; echo "thin rc=$?"
 if [ "$2" != "noncu" ]; then
 # every launch of ~1.5 steps with its device time and DRAM traffic (cold-cache, serialised: compare SHARES)
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1300 -c 700 --csv \
@@ -20,4 +24,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgra
     python tests/dev_prof_wgrad.py > gpurun_out/${tag}_ncu_wgrad.log 2>&1; echo "ncu wgrad rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:bn_bwd -s 4 -c 4 -f -o gpurun_out/${tag}_bn_bwd \
     python tests/dev_bn_prof.py > gpurun_out/${tag}_ncu_bnbwd.log 2>&1; echo "ncu bn_bwd rc=$?"
+# the HBM-bound ends: thin-input convolution, thin weight gradient (both operand roles), decoder head
+timeout 300 ncu --set full --clock-control none --import-source on -k 'regex:thin_|decoder_head' -s 8 -c 6 -f -o gpurun_out/${tag}_thin \
+    python tests/dev_thin.py > gpurun_out/${tag}_ncu_thin.log 2>&1; echo "ncu thin rc=$?"
 fi
