@@ -895,13 +895,21 @@ extern "C" int srvp_channel_stats(const srvp_bf16* z, int64_t rows, int32_t C, f
 
 // Grid: enough blocks to fill the machine whatever the channel count (a block walks items_per_block pixels x C/8 chunks with 256
 // threads: ~8 loop iterations per thread), bounded by 2048 and by the size of the partial-sum buffer (blocks x C x 2 floats).
+namespace srvp { int num_sms_cached(); }
+using srvp::num_sms_cached;
+
 static int bn_bwd_blocks(long long items, int C, int da_mode) {
   const int U = (da_mode == SRVP_SRC_DIRECT) ? 4 : 2;
   const long long chunk_items = items * (C / 8);
   long long nb = (chunk_items + 256LL * U * 8 - 1) / (256LL * U * 8);
   const long long cap = (1 << 20) / C;
   if (nb > cap) nb = cap;
-  if (nb > 2048) nb = 2048;   // the finalisation walks one partial row per block with 8 row lanes: keep it short
+  // The finalisation walks one partial row per block with 8 row lanes and sits on the critical path between the two passes: with 2048
+  // rows it took 63 us per layer (profiles/r04k_launch_summary_bench.csv: 1.1 ms per step); four blocks per SM keep the HBM-bound passes
+  // just as busy (grid-stride loops) and make it three times shorter.
+  const long long per_sm_cap = (da_mode == SRVP_SRC_POOL2 ? 6LL : 4LL) * num_sms_cached();   // whole waves: 3 (pooled kernel) / 2 resident blocks per SM
+  if (nb > per_sm_cap) nb = per_sm_cap;
+  if (nb > 2048) nb = 2048;
   if (nb < 1) nb = 1;
   return (int)nb;
 }

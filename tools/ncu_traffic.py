@@ -10,7 +10,8 @@ import os
 import re
 import sys
 
-FAMILIES = [('conv3x3', r'conv3x3_kernel'), ('wgrad3x3', r'wgrad3x3_kernel'), ('bn_bwd', r'bn_bwd_(flat_)?kernel'), ('gemm', r'gemm_kernel'),
+FAMILIES = [('conv3x3', r'conv3x3_kernel|thin_conv_kernel'), ('wgrad3x3', r'wgrad3x3_(tma_)?kernel|thin_wgrad_kernel'), ('bn_bwd', r'bn_bwd_(flat_|pool_)?kernel'),
+            ('decoder_head', r'decoder_head_kernel'), ('gemm', r'gemm_kernel'),
             ('latent_fwd', r'latent_fwd_kernel'), ('latent_bwd', r'latent_bwd_kernel'), ('linear_f32', r'linear_f32_kernel')]
 
 
