@@ -216,6 +216,139 @@ __global__ void __launch_bounds__(1024) lstm_bwd_kernel(const float* __restrict_
   }
 }
 
+// Same recurrences with FOUR threads per hidden unit (H <= 256: 4H <= 1024 threads): thread (j, q) reduces quarter q of the
+// contraction for all VB = 4 videos, the partial sums meet in shared memory, and thread (j, q) then does the pointwise gate math of
+// video q. The one-thread-per-unit kernels above walk the whole contraction with 4 - 16 loads in flight and are bound by the L2
+// latency of the W_hh stream (0.51 / 0.79 ms per launch at T = 12, H = 256, profiles/r04k_launch_summary_bench.csv): a quarter of
+// the chain per thread and eight to sixteen independent loads per iteration cut that to a third.
+__global__ void __launch_bounds__(1024) lstm_fwd4_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, float* __restrict__ h_all,
+                                                         float* __restrict__ c_all, float* __restrict__ gates, int T, int B, int H) {
+  extern __shared__ float sm4[];
+  float* hs = sm4;                 // [VB][H]
+  float* part = sm4 + VB * H;      // [4 quarters][VB * 4 (video, gate)][H]
+  const int j = threadIdx.x % H, q = threadIdx.x / H, b0 = blockIdx.x * VB;
+  const int H4 = 4 * H, kq = H / 4;
+  float c = 0.f;                   // cell state of (unit j, video q)
+  if (q == 0) {
+#pragma unroll
+    for (int v = 0; v < VB; ++v) hs[v * H + j] = 0.f;
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    if (t > 0) {  // h_0 = 0
+      float acc[VB][4];
+#pragma unroll
+      for (int v = 0; v < VB; ++v)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[v][g] = 0.f;
+      for (int k = q * kq; k < (q + 1) * kq; k += 4) {
+        float w[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) w[kk][g] = __ldg(whhT + (size_t)(k + kk) * H4 + g * H + j);
+#pragma unroll
+        for (int v = 0; v < VB; ++v) {
+          const float4 hv = *reinterpret_cast<const float4*>(hs + v * H + k);
+          const float h4[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) acc[v][g] = fmaf(h4[kk], w[kk][g], acc[v][g]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VB; ++v)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) part[((size_t)q * (VB * 4) + v * 4 + g) * H + j] = acc[v][g];
+    }
+    __syncthreads();  // partial sums complete, everyone has finished reading h_{t-1}
+    {
+      const int v = q, b = min(b0 + v, B - 1);
+      const float* xp = xproj + ((size_t)t * B + b) * H4 + j;
+      float a[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        a[g] = __ldg(xp + g * H);
+        if (t > 0) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) a[g] += part[((size_t)qq * (VB * 4) + v * 4 + g) * H + j];
+        }
+      }
+      const float ig = sigmoidf_(a[0]), fg = sigmoidf_(a[1]), gg = tanhf(a[2]), og = sigmoidf_(a[3]);
+      c = fmaf(fg, c, ig * gg);
+      const float h = og * tanhf(c);
+      hs[v * H + j] = h;
+      if (b0 + v < B) {
+        const size_t row = (size_t)t * B + b0 + v;
+        h_all[row * H + j] = h;
+        c_all[row * H + j] = c;
+        float* gp = gates + row * H4 + j;
+        gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) lstm_bwd4_kernel(const float* __restrict__ dh_all, const float* __restrict__ gates, const float* __restrict__ c_all,
+                                                         const float* __restrict__ whh, float* __restrict__ dgates, int T, int B, int H) {
+  extern __shared__ float sm4[];
+  float* dga = sm4;                  // [VB][4H]
+  float* part = sm4 + VB * 4 * H;    // [4 quarters][VB][H]
+  const int j = threadIdx.x % H, q = threadIdx.x / H, b0 = blockIdx.x * VB;
+  const int H4 = 4 * H;
+  float dh_rec = 0.f, dc_next = 0.f;   // of (unit j, video q)
+  for (int t = T - 1; t >= 0; --t) {
+    {
+      const int v = q, b = b0 + v;
+      float da[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b < B) {
+        const size_t row = (size_t)t * B + b;
+        const float* gp = gates + row * H4 + j;
+        const float ig = gp[0], fg = gp[H], gg = gp[2 * H], og = gp[3 * H];
+        const float ct = c_all[row * H + j];
+        const float cprev = t > 0 ? c_all[((size_t)(t - 1) * B + b) * H + j] : 0.f;
+        const float dh = dh_all[row * H + j] + dh_rec;
+        const float tc = tanhf(ct);
+        const float dc = fmaf(dh * og, 1.f - tc * tc, dc_next);
+        dc_next = dc * fg;
+        da[0] = dc * gg * ig * (1.f - ig);
+        da[1] = dc * cprev * fg * (1.f - fg);
+        da[2] = dc * ig * (1.f - gg * gg);
+        da[3] = dh * tc * og * (1.f - og);
+        float* dp = dgates + row * H4 + j;
+        dp[0] = da[0]; dp[H] = da[1]; dp[2 * H] = da[2]; dp[3 * H] = da[3];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dga[v * H4 + g * H + j] = da[g];
+    }
+    __syncthreads();
+    if (t > 0) {
+      // dh_{t-1}[j] = sum_n W_hh[n][j] * da[n]: quarter q = the rows of gate q
+      float acc[VB];
+#pragma unroll
+      for (int v = 0; v < VB; ++v) acc[v] = 0.f;
+      for (int n = q * H; n < (q + 1) * H; n += 8) {
+        float w[8];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) w[nn] = __ldg(whh + (size_t)(n + nn) * H + j);
+#pragma unroll
+        for (int v = 0; v < VB; ++v) {
+          const float4 d0 = *reinterpret_cast<const float4*>(dga + v * H4 + n), d1 = *reinterpret_cast<const float4*>(dga + v * H4 + n + 4);
+          acc[v] = fmaf(d0.x, w[0], acc[v]); acc[v] = fmaf(d0.y, w[1], acc[v]); acc[v] = fmaf(d0.z, w[2], acc[v]); acc[v] = fmaf(d0.w, w[3], acc[v]);
+          acc[v] = fmaf(d1.x, w[4], acc[v]); acc[v] = fmaf(d1.y, w[5], acc[v]); acc[v] = fmaf(d1.z, w[6], acc[v]); acc[v] = fmaf(d1.w, w[7], acc[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VB; ++v) part[((size_t)q * VB + v) * H + j] = acc[v];
+      __syncthreads();
+      dh_rec = (part[((size_t)0 * VB + q) * H + j] + part[((size_t)1 * VB + q) * H + j]) + (part[((size_t)2 * VB + q) * H + j] + part[((size_t)3 * VB + q) * H + j]);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 }  // namespace srvp
 
@@ -249,6 +382,13 @@ extern "C" int srvp_lstm_fwd(const float* xproj, const float* whh_t, float* h_al
                              void* stream) {
   SRVP_REQUIRE(H % 32 == 0 && H <= 1024 && H >= 32, "lstm_fwd: hidden size %d must be a multiple of 32, <= 1024", H);
   SRVP_REQUIRE(T > 0 && B > 0, "lstm_fwd: empty sequence");
+  if (H <= 256 && H % 8 == 0 && VB == 4) {
+    const size_t smem = (size_t)(VB * H + 4 * VB * 4 * H) * sizeof(float);     // 68 KB at H = 256
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(lstm_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); attr = true; }
+    lstm_fwd4_kernel<<<(B + VB - 1) / VB, 4 * H, smem, (cudaStream_t)stream>>>(xproj, whh_t, h_all, c_all, gates, T, B, H);
+    return check_launch("lstm_fwd");
+  }
   lstm_fwd_kernel<<<(B + VB - 1) / VB, H, (size_t)VB * H * sizeof(float), (cudaStream_t)stream>>>(xproj, whh_t, h_all, c_all, gates, T, B, H);
   return check_launch("lstm_fwd");
 }
@@ -257,6 +397,11 @@ extern "C" int srvp_lstm_bwd(const float* dh_all, const float* gates, const floa
                              int32_t H, void* stream) {
   SRVP_REQUIRE(H % 32 == 0 && H <= 1024 && H >= 32, "lstm_bwd: hidden size %d must be a multiple of 32, <= 1024", H);
   SRVP_REQUIRE(T > 0 && B > 0, "lstm_bwd: empty sequence");
+  if (H <= 256 && H % 8 == 0 && VB == 4) {
+    const size_t smem = (size_t)(VB * 4 * H + 4 * VB * H) * sizeof(float);     // 32 KB at H = 256
+    lstm_bwd4_kernel<<<(B + VB - 1) / VB, 4 * H, smem, (cudaStream_t)stream>>>(dh_all, gates, c_all, whh, dgates, T, B, H);
+    return check_launch("lstm_bwd");
+  }
   lstm_bwd_kernel<<<(B + VB - 1) / VB, H, (size_t)VB * 4 * H * sizeof(float), (cudaStream_t)stream>>>(dh_all, gates, c_all, whh, dgates, T, B, H);
   return check_launch("lstm_bwd");
 }
