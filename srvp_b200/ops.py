@@ -30,7 +30,8 @@ def profiled(name):
                 e0.record()
                 out = fn(*args, **kwargs)
                 e1.record()
-                TIMELINE.append((name, PROFILE_TAG, 'side' if torch.cuda.current_stream() in _SIDE_STREAMS.values() else 'main', e0, e1))
+                cs = torch.cuda.current_stream()
+                TIMELINE.append((name, PROFILE_TAG, 'side' if cs in _SIDE_STREAMS.values() else 'aux' if cs in _AUX_STREAMS.values() else 'main', e0, e1))
                 return out
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -321,6 +322,21 @@ def _side_stream():
     return s
 
 
+_AUX_STREAMS = {}
+_AUX_BUSY = [False]
+
+
+def _aux_stream():
+    """Third stream, for the SMALL off-critical-path kernels of side_section(): on the weight-gradient stream they sat in front of the
+    encoder's weight gradients and, since a small kernel only gets SMs between two persistent convolutions of the main stream, held them
+    back by ~4 ms (profiles/r04o_timeline.log)."""
+    dev = torch.cuda.current_device()
+    s = _AUX_STREAMS.get(dev)
+    if s is None:
+        s = _AUX_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def flush_wgrads(held=False):
     """Issue the recorded weight-gradient launches on the side stream, behind everything enqueued on the current stream so far.
     held=True also issues the launches recorded with hold=True, each limited to HELD_MAX_CTAS CTAs."""
@@ -365,14 +381,14 @@ def side_section(*keep):
     if not (WGRAD_STREAM and DEFER_JOIN and PROFILE is None) or torch.cuda.is_current_stream_capturing():
         yield False
         return
-    side = _side_stream()
+    aux = _aux_stream()
     ev = torch.cuda.Event()
     ev.record()
-    side.wait_event(ev)
-    with torch.cuda.stream(side):
+    aux.wait_event(ev)
+    with torch.cuda.stream(aux):
         yield True
     _INFLIGHT.append(keep)
-    _SIDE_BUSY[0] = True
+    _AUX_BUSY[0] = True
 
 
 def after_side(fn):
@@ -385,6 +401,8 @@ def after_side(fn):
     flush_wgrads(held=True)
     side = _side_stream()
     side.wait_stream(torch.cuda.current_stream())
+    if _AUX_BUSY[0]:
+        side.wait_stream(_aux_stream())
     with torch.cuda.stream(side):
         r = fn()
     _SIDE_BUSY[0] = True
@@ -397,6 +415,9 @@ def join_wgrads():
     if _SIDE_BUSY[0]:
         torch.cuda.current_stream().wait_stream(_side_stream())
         _SIDE_BUSY[0] = False
+    if _AUX_BUSY[0]:
+        torch.cuda.current_stream().wait_stream(_aux_stream())
+        _AUX_BUSY[0] = False
     _INFLIGHT.clear()              # later work on this stream is ordered behind the side stream: the buffers may be re-used
 
 

@@ -51,6 +51,6 @@ for s, e, name, tag, strm in rows:
     if strm == 'side':
         ov = sum(max(0.0, min(e, me) - max(s, ms)) for ms, me in main)
         extra = f'  under main-stream kernels: {ov:.3f} ms'
-    print(f'{"        " if strm == "side" else ""}{s:8.3f} -> {e:8.3f}  ({e - s:6.3f})  {strm:4s} {name:14s} {tag}{extra}')
+    print(f'{"        " if strm == "side" else "                " if strm == "aux" else ""}{s:8.3f} -> {e:8.3f}  ({e - s:6.3f})  {strm:4s} {name:14s} {tag}{extra}')
 side_busy = sum(e - s for s, e, n, t, st in rows if st == 'side')
 print(f'side stream busy {side_busy:.3f} ms')
