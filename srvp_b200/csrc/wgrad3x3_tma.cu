@@ -42,7 +42,8 @@ struct WgTmaDev {
   int F, H, W, Wp;
   int RB, HB, NSUB;          // image rows per stripe, stripes per frame, stripes per pipeline stage
   int total_subs;            // F * HB
-  int stages_total, splits;
+  int stages_total, splits;  // splits: informational (work units per channel-block pair / units per CTA)
+  long long total_units;     // pairs * stages_total pipeline stages, dealt out evenly over the grid (a CTA's range may span 2-3 pairs)
   int num_mblk, num_nblk;    // 64-channel blocks of the activation / dz operand
   int ksteps;                // MMA K steps (16 pixels) per stripe
   int nb;                    // MMA N = dz channels per CTA: 64, or 16 for a thin dz (the decoder's last layer)
@@ -68,7 +69,7 @@ __device__ __forceinline__ uint64_t sw128_desc_hi(uint32_t lbo16) {
   return ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-__global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_dz,
+__global__ void __maxnreg__(120) wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_dz,
                                                                      const WgTmaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -76,12 +77,14 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
   uint64_t* full = bars;                // [kMaxStg]
   uint64_t* empty = bars + kMaxStg;     // [kMaxStg]
   uint64_t* acc_full = bars + 2 * kMaxStg;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStg + 1);
+  uint64_t* acc_empty = bars + 2 * kMaxStg + 1;   // epilogue done with the accumulators AND the pipeline buffers it stages through
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStg + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < p.nstg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -98,31 +101,50 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
     __trap();
   }
 
-  const int pairs = p.num_mblk * p.num_nblk;
-  const int pair = blockIdx.x % pairs, split = blockIdx.x / pairs;
-  const int mblk = pair / p.num_nblk, nblk = pair % p.num_nblk;
-  const int steps_per = (p.stages_total + p.splits - 1) / p.splits;
-  const int s0 = split * steps_per;
-  const int s1 = min(p.stages_total, s0 + steps_per);
-  const int nst = max(0, s1 - s0);
+  // Work = (channel-block pair, pipeline stage) units in pair-major order, dealt out EVENLY over the grid ("stream-K"): with whole
+  // K-splits per pair the 512-channel layers (64 pairs x 2 splits) kept 128 of the 148 SMs busy. A CTA walks its range segment by
+  // segment; a segment is a run of stages of one pair and ends with its own epilogue (split-K partial sums added with red).
+  const long long u_begin = p.total_units * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long u_end = p.total_units * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  // segment iteration shared by the three roles
+  struct Seg { int mblk, nblk, s0, n; };
+  auto next_seg = [&](long long& u, Seg& sg) -> bool {
+    if (u >= u_end) return false;
+    const int pair = (int)(u / p.stages_total);
+    sg.s0 = (int)(u - (long long)pair * p.stages_total);
+    const long long left = u_end - u;
+    sg.n = (int)(left < (long long)(p.stages_total - sg.s0) ? left : (long long)(p.stages_total - sg.s0));
+    sg.mblk = pair / p.num_nblk;
+    sg.nblk = pair % p.num_nblk;
+    u += sg.n;
+    return true;
+  };
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && nst > 0) {
-      for (int i = 0; i < nst; ++i) {
-        const int st = i % p.nstg;
-        mbar_wait(&empty[st], ((i / p.nstg) & 1) ^ 1);
-        if (p.dbg & 1) { mbar_arrive(&full[st]); continue; }
-        mbar_arrive_expect_tx(&full[st], p.tx_bytes);
-        uint8_t* sb = tiles + (size_t)st * p.stage_bytes;
-        for (int j = 0; j < p.NSUB; ++j) {
-          const int t = (s0 + i) * p.NSUB + j;
-          int f = t / p.HB;
-          int y0 = (t - f * p.HB) * p.RB;
-          if (t >= p.total_subs) { f = p.F; y0 = 0; }   // past the last stripe: a box entirely out of bounds = zeros
-          tma_load_4d(sb + (size_t)j * p.sub_bytes, &map_act, &full[st], mblk * 64, -1, y0 - 1, f);
-          tma_load_4d(sb + (size_t)j * p.sub_bytes + p.a_block_bytes, &map_dz, &full[st], nblk * 64, 0, y0, f);
+    if (lane == 0) {
+      long long u = u_begin;
+      Seg sg;
+      uint32_t it = 0;     // stage counter over all segments: ring position and phase
+      int seg = 0;
+      while (next_seg(u, sg)) {
+        if (seg > 0) mbar_wait(acc_empty, (seg - 1) & 1);   // the previous epilogue stages through the pipeline buffers
+        for (int i = 0; i < sg.n; ++i, ++it) {
+          const int st = it % p.nstg;
+          mbar_wait(&empty[st], ((it / p.nstg) & 1) ^ 1);
+          if (p.dbg & 1) { mbar_arrive(&full[st]); continue; }
+          mbar_arrive_expect_tx(&full[st], p.tx_bytes);
+          uint8_t* sb = tiles + (size_t)st * p.stage_bytes;
+          for (int j = 0; j < p.NSUB; ++j) {
+            const int t = (sg.s0 + i) * p.NSUB + j;
+            int f = t / p.HB;
+            int y0 = (t - f * p.HB) * p.RB;
+            if (t >= p.total_subs) { f = p.F; y0 = 0; }   // past the last stripe: a box entirely out of bounds = zeros
+            tma_load_4d(sb + (size_t)j * p.sub_bytes, &map_act, &full[st], sg.mblk * 64, -1, y0 - 1, f);
+            tma_load_4d(sb + (size_t)j * p.sub_bytes + p.a_block_bytes, &map_dz, &full[st], sg.nblk * 64, 0, y0, f);
+          }
         }
+        ++seg;
       }
     }
   } else if (warp == 5) {
@@ -134,7 +156,7 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
     // TMEM column; per K step only one 32-bit add per descriptor remains.
     // The WHOLE warp runs the loop converged and only the tcgen05 instructions are predicated on one elected lane: inside a
     // `lane == 0` branch the compiler cannot use the uniform datapath and wraps every MMA in an elect / R2UR broadcast loop.
-    if (nst > 0) {
+    {
       const uint32_t idesc = umma_idesc_bf16(128, p.nb, 1, 1);
       const uint32_t tile0 = smem_u32(tiles) >> 4;
       uint32_t a_lo[kMaxOps], a_hi[kMaxOps], dcol[kMaxOps];
@@ -152,10 +174,18 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
       const uint32_t stage16 = p.stage_bytes >> 4, sub16 = p.sub_bytes >> 4;
       const int nsub = p.NSUB, ksteps = p.ksteps, nstg = p.nstg;
       const bool no_mma = (p.dbg & 2) != 0;
-      uint32_t accf = 0;
       int st = 0;
       uint32_t ph = 0;
-      for (int i = 0; i < nst; ++i) {
+      long long u = u_begin;
+      Seg sg;
+      int seg = 0;
+      while (next_seg(u, sg)) {
+      if (seg > 0) {      // the epilogue of the previous segment has read the accumulators
+        mbar_wait(acc_empty, (seg - 1) & 1);
+        tc_fence_after();
+      }
+      uint32_t accf = 0;
+      for (int i = 0; i < sg.n; ++i) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
         uint32_t off = (uint32_t)st * stage16;
@@ -176,12 +206,19 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
         if (++st == nstg) { st = 0; ph ^= 1u; }
       }
       if (elect_one_sync()) umma_commit(acc_full);
+      ++seg;
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> shared memory -> coalesced red.add into dW
-    if (nst > 0 && !(p.dbg & 8)) {
-      mbar_wait(acc_full, 0);
+    long long u = u_begin;
+    Seg sg;
+    int seg = 0;
+    while (next_seg(u, sg)) {
+      const int mblk = sg.mblk, nblk = sg.nblk;
+      mbar_wait(acc_full, seg & 1);
       tc_fence_after();
+      if (!(p.dbg & 8)) {
       const int L = warp * 32 + lane;
       const int tb = L >> 6;
       const int cl = L & 63;
@@ -246,6 +283,18 @@ __global__ void __launch_bounds__(kTThreads, 1) wgrad3x3_tma_kernel(const __grid
           }
         }
       }
+      }   // !(dbg & 8)
+      // hand the accumulators and the pipeline buffers (staging area of the fast path) back. Rows of the tiles that no TMA box writes
+      // (K padding, tap over-run) must read as zeros again: the staged fp32 values would otherwise meet the next segment's MMAs as
+      // arbitrary bf16 bit patterns (0 x NaN). The TMA producer writes through the async proxy: generic-proxy accesses are fenced first.
+      if (u < u_end) {
+        named_bar_sync(1, 128);     // every epilogue thread has finished reading the staging area
+        for (size_t i = warp * 32 + lane; i < (size_t)p.nstg * p.stage_bytes / 16; i += 128) reinterpret_cast<uint4*>(tiles)[i] = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      ++seg;
     }
   }
   tc_fence_before();
@@ -337,10 +386,11 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
   int sms = num_sms_cached();
   if (a->max_ctas > 0 && a->max_ctas < sms) sms = a->max_ctas;
   const int pairs = d.num_mblk * d.num_nblk;
-  int splits = sms / pairs;
-  if (splits < 1) splits = 1;
-  if (splits > d.stages_total) splits = d.stages_total;
-  d.splits = splits;
+  d.total_units = (long long)pairs * d.stages_total;
+  long long grid_ll = sms;                       // one CTA per SM, every CTA the same number of stages (+-1)
+  if (grid_ll > d.total_units) grid_ll = d.total_units;
+  const int grid = (int)grid_ll;
+  d.splits = (grid + pairs - 1) / pairs;
   // tap pairs: (0,1) (3,4) (6,7) one pixel apart, (2,5) one image row apart, 8 alone
   const int pa[5] = {0, 3, 6, 2, 8}, pb[5] = {1, 4, 7, 5, -1};
   d.nops = 5;
@@ -365,7 +415,7 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
   CUtensorMap map_act, map_dz;
   if (make_map(&map_act, reinterpret_cast<const uint16_t*>(a->act) + a->act_coff, a->act_channels, a->act_cpitch, a->W, a->H, a->frames, RB + 2) != 0) return -1;
   if (make_map(&map_dz, reinterpret_cast<const uint16_t*>(a->dz) + a->dz_coff, a->dz_channels, a->dz_cpitch, a->W, a->H, a->frames, RB) != 0) return -1;
-  const size_t smem = (size_t)nstg * d.stage_bytes + 1024 /* alignment slack */ + (2 * kMaxStg + 2) * 8;
+  const size_t smem = (size_t)nstg * d.stage_bytes + 1024 /* alignment slack */ + (2 * kMaxStg + 3) * 8;
   SRVP_REQUIRE(smem <= 227 * 1024, "wgrad3x3_tma: shared memory %zu B exceeds 227 KB", smem);
   static bool attr = false;
   if (!attr) {
@@ -374,7 +424,7 @@ int wgrad3x3_tma_try(const srvp_wgrad3x3_args* a, cudaStream_t stream) {
     attr = true;
   }
   size_t smem_launch = smem < 120 * 1024 ? 120 * 1024 : smem;   // one CTA per SM (all 512 TMEM columns are allocated)
-  wgrad3x3_tma_kernel<<<pairs * splits, kTThreads, smem_launch, stream>>>(map_act, map_dz, d);
+  wgrad3x3_tma_kernel<<<grid, kTThreads, smem_launch, stream>>>(map_act, map_dz, d);
   const int rc = check_launch("wgrad3x3_tma");
   return rc != 0 ? rc : 1;
 }
