@@ -58,26 +58,33 @@ __device__ __forceinline__ void load_tile(uint8_t* tile, const void* base, int i
                                           int K, int lt) {
   if (s_k == 1) {
     // K-major: [8 k-chunks][128 rows][8]; this thread owns row `lt`
+    // all eight loads first, then the stores: interleaved, every shared-memory store (a possible alias of the generic source pointer)
+    // pinned the next global load behind it and a K step cost eight dependent L2 round trips per operand
     const int row = row0 + lt;
     const bool rv = row < nrows;
+    uint4 r[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + j * 8;
       const int nv = rv ? min(8, K - k) : 0;
-      *reinterpret_cast<uint4*>(tile + ((size_t)j * 128 + lt) * 16) = load8(base, is_f32, (long long)row * s_row + k, nv);
+      r[j] = load8(base, is_f32, (long long)row * s_row + k, nv);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(tile + ((size_t)j * 128 + lt) * 16) = r[j];
   } else {
     // MN-major: [16 row-chunks][64 k][8]; this thread owns k-row (lt % 64) and 8 of the 16 row chunks
     const int kr = lt & 63, half = lt >> 6;
     const int k = k0 + kr;
     const bool kv = k < K;
+    uint4 r[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const int j = half * 8 + jj;
-      const int row = row0 + j * 8;
+      const int row = row0 + (half * 8 + jj) * 8;
       const int nv = kv ? min(8, nrows - row) : 0;
-      *reinterpret_cast<uint4*>(tile + ((size_t)j * 64 + kr) * 16) = load8(base, is_f32, (long long)k * s_k + row, nv);
+      r[jj] = load8(base, is_f32, (long long)k * s_k + row, nv);
     }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(tile + ((size_t)(half * 8 + jj) * 64 + kr) * 16) = r[jj];
   }
 }
 
@@ -151,6 +158,33 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmDev p) 
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(acc + c0, v);
+      // Vector path: a thread owns a row, its 32 columns are contiguous in C when c_sn == 1 -- plain stores go out as 16-byte pieces
+      // (bf16: 4, fp32: 8 per batch). Element-wise 2-byte stores made every warp instruction touch 32 sectors with 2 useful bytes each:
+      // the (2304 x 8192) bf16 outputs of the 4x4 (de)convolution heads took 230 - 310 us instead of ~40 (profiles/r04k_launches_bench.csv.gz).
+      if (m < p.M && p.c_sn == 1 && n0 + c0 + 32 <= p.N && !(p.c_f32 && (gridDim.z > 1 && p.c_split_stride == 0)) && !(p.c_f32 && p.accumulate)) {
+        const long long idx = (long long)m * p.c_sm + (long long)(n0 + c0) + (long long)blockIdx.z * p.c_split_stride;
+        char* dstb = reinterpret_cast<char*>(p.c) + idx * (p.c_f32 ? 4 : 2);
+        if ((reinterpret_cast<uintptr_t>(dstb) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] + bias_m;
+            if (add_bias && !p.bias_on_m) x += __ldg(p.bias + n0 + c0 + j);
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            else if (p.act == 2) x = tanhf(x);
+            v[j] = x;
+          }
+          if (p.c_f32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dstb)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              reinterpret_cast<uint4*>(dstb)[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                             pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          }
+          continue;
+        }
+      }
       if (m < p.M) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
