@@ -16,6 +16,7 @@ Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JS
   --workload human_rollout: the evaluation rollout of configs[4] (test.py: 16 videos x 100 samples, 8 -> 53 frames, 2 Euler steps)
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -169,6 +170,10 @@ def run_ours(args):
     def timed(x, steps, hosts=None):
         """(ms, last loss value): `steps` training steps, device-timed; hosts: e2e mode (H2D of the uint8 batch + D2H of the loss per step)."""
         barrier()
+        # the host enqueues ~300 launches per step ahead of the device: a generation-2 pass of Python's cyclic garbage collector in the
+        # middle of the timed loop (50 - 300 ms with the whole torch object graph alive) starves it. Collect now, not while timing.
+        gc.collect()
+        gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lv = None
         e0.record()
@@ -180,6 +185,7 @@ def run_ours(args):
                 lv = step(xb).item()
         e1.record()
         barrier()
+        gc.enable()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -8,6 +8,8 @@ import ctypes
 
 import torch
 
+from . import ops
+
 from . import _lib
 from ._lib import c_int, c_i64, check, lib, ptr, stream_ptr
 from .ops import profiled, transpose_last2
@@ -52,6 +54,20 @@ def matmul_f32(a, b, c, *, bias=None, bias2=None, act=_lib.ACT_NONE, accumulate=
     return c
 
 
+def _direct_sinks(*params):
+    """The GradBucket views of the given parameters when ALL of them accumulate in place (ops.grad_target semantics), else None."""
+    out = []
+    for p in params:
+        if p is None:
+            out.append(None)
+            continue
+        v = getattr(p, '_srvp_sink', None)
+        if v is None or p.grad is not v or not p.requires_grad:
+            return None
+        out.append(v)
+    return out
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) on (rows, din) fp32 (nn.Linear [+ ReLU / Tanh])."""
 
@@ -61,6 +77,7 @@ class LinearFn(torch.autograd.Function):
         y = torch.empty(x.shape[0], weight.shape[0], dtype=torch.float32, device=x.device)
         matmul_f32(x, weight, y, bias=bias, act=act)
         ctx.act = act
+        ctx.bias = bias
         ctx.save_for_backward(x, weight, y)
         return y
 
@@ -76,6 +93,18 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             matmul_f32(dy, weight.t(), dx)                      # dx[m, k] = sum_n dy[m, n] W[n, k]
+        bias = ctx.bias
+        sinks = _direct_sinks(weight, bias) if ctx.needs_input_grad[1] else None
+        if sinks is not None:
+            # every gradient of this layer lives in the GradBucket: the parameter gradients (a reduction over all T*B rows that
+            # nothing on the critical path reads) are accumulated in place on the auxiliary stream (ops.side_section)
+            with ops.side_section(dy, x):
+                tmp = torch.empty_like(weight)
+                matmul_f32(dy.t(), x.t(), tmp)
+                sinks[0].add_(tmp)
+                if bias is not None:
+                    colsum(dy, sinks[1])
+            return dx, None, None, None
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(weight)
             matmul_f32(dy.t(), x.t(), dw)                       # dW[n, k] = sum_m dy[m, n] x[m, k]
@@ -118,6 +147,7 @@ class LSTMFn(torch.autograd.Function):
         check(lib().srvp_lstm_fwd(ptr(xproj), ptr(whh_t), ptr(h_all), ptr(c_all), ptr(gates), c_int(T), c_int(B), c_int(H), stream_ptr()),
               'lstm_fwd')
         ctx.save_for_backward(x2, w_ih, w_hh, h_all, c_all, gates)
+        ctx.biases = (b_ih, b_hh)
         ctx.dims = (T, B, I, H)
         return h_all
 
@@ -135,6 +165,19 @@ class LSTMFn(torch.autograd.Function):
             dx = torch.empty(T * B, I, dtype=torch.float32, device=dev)
             matmul_f32(dg2, w_ih.t(), dx)
             dx = dx.view(T, B, I)
+        sinks = _direct_sinks(w_ih, w_hh, *ctx.biases)
+        if sinks is not None:
+            with ops.side_section(dg2, x2, h_all):      # see LinearFn.backward
+                tmp = torch.empty_like(w_ih)
+                matmul_f32(dg2.t(), x2.t(), tmp)
+                sinks[0].add_(tmp)
+                if T > 1:
+                    tmp2 = torch.empty_like(w_hh)
+                    matmul_f32(dg2[B:].t(), h_all.view(T * B, H)[:(T - 1) * B].t(), tmp2)
+                    sinks[1].add_(tmp2)
+                colsum(dg2, sinks[2])
+                colsum(dg2, sinks[3])
+            return dx, None, None, None, None
         dw_ih = torch.empty_like(w_ih)
         matmul_f32(dg2.t(), x2.t(), dw_ih)
         dw_hh = torch.zeros_like(w_hh)
