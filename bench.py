@@ -216,6 +216,7 @@ def run_ours(args):
     ms, _ = timed(xdev, args.steps)
     launches = _lib.lib().srvp_launch_count() - launches0
     ms_e2e, lv = timed(xdev, args.steps, hosts=host)
+    side_per_step = (ops.SIDE_LAUNCHES[0] - side0) // max(1, args.steps * 2)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -306,7 +307,7 @@ def run_ours(args):
                          d2h_bytes_per_step=4),
                 gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline, conv_stages=stages, hbm_kernels=hbm,
                 kernel_breakdown=breakdown,
-                streams=dict(weight_gradient_stream=bool(ops.WGRAD_STREAM), side_launches_per_step=(ops.SIDE_LAUNCHES[0] - side0) // max(1, args.steps * 2),
+                streams=dict(weight_gradient_stream=bool(ops.WGRAD_STREAM), side_launches_per_step=side_per_step,
                              sum_kernel_ms_serialised=round(tot_ms / 2, 3),
                              note='timed steps: weight gradients (and, under the GradBucket, the head / latent weight-gradient GEMMs) run on a second '
                                   'stream next to the HBM-bound batch-norm backward and the few-CTA latent / inference backward kernels '

@@ -135,7 +135,20 @@ def check(rc, what=''):
 
 
 def stream_ptr():
-    return c_ptr(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device. The raw C accessors: torch.cuda.current_stream() builds a Stream
+    object through several Python layers (device-index resolution, is_available(), an os.environ lookup) -- 280 calls per training
+    step were a quarter of the host time per step (tools/host_profile.py)."""
+    return c_ptr(_raw_stream(_raw_device()))
+
+
+try:
+    _raw_stream, _raw_device = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+except AttributeError:      # older / newer torch without the private accessors
+    def _raw_device():
+        return torch.cuda.current_device()
+
+    def _raw_stream(_dev):
+        return torch.cuda.current_stream().cuda_stream
 
 
 def ptr(t):

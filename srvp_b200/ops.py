@@ -458,11 +458,12 @@ def wgrad3x3(act, act_channels, dz, dz_channels, frames, H, W, cout, cin, dw, ki
         (_HELD if hold and DEFER_JOIN else _DEFERRED).append((a, keep))
     else:
         check(lib().srvp_wgrad3x3(ctypes.byref(a), stream_ptr()), 'wgrad3x3')
-    fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
-    # thin operands (first encoder / last decoder layer): HBM-bound, also listed by themselves (bench.py hbm_kernels)
-    sub = f'hbm:wgrad_thin[{PROFILE_TAG}]' if min(dz_channels, act_channels) <= 16 else None
-    _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx, sub=sub,
-             desc=f'F={frames} {H}x{W} act{act_channels} x dz{dz_channels}' + (' map4' if map4 else ''))
+    if PROFILE is not None:
+        fx = 2.0 * frames * H * W * cout * cin * (4 if map4 else 9)
+        # thin operands (first encoder / last decoder layer): HBM-bound, also listed by themselves (bench.py hbm_kernels)
+        sub = f'hbm:wgrad_thin[{PROFILE_TAG}]' if min(dz_channels, act_channels) <= 16 else None
+        _account(fx * alg_scale, 2.0 * frames * H * W * (cout + cin) + 4.0 * dw.numel(), executed=fx, sub=sub,
+                 desc=f'F={frames} {H}x{W} act{act_channels} x dz{dz_channels}' + (' map4' if map4 else ''))
     return dw
 
 
@@ -529,6 +530,8 @@ def conv3x3(srcs, wpack, frames, H, W, cout, *, out=None, out_cpitch=None, out_c
     if save_input:
         a.a_out, a.a_out_cpitch, a.a_out_channels = ptr(a_out), a_out.shape[-1], a_out_channels
     check(lib().srvp_conv3x3(ctypes.byref(a), stream_ptr()), 'conv3x3')
+    if PROFILE is None:          # the accounting below is only read by bench.py's per-launch profile
+        return (out, stats_partial, a_out) if save_input else (out, stats_partial)
     cin_real = cin_real if cin_real is not None else sum(s.channels for s in srcs)
     obytes = (out.numel() * out.element_size()) if not out_xstride else 2.0 * frames * H * W * cout
     fx = 2.0 * frames * H * W * cout * cin_real * taps
@@ -751,17 +754,19 @@ def bn_bwd(z, state, gamma, dgamma, dbeta, da, da_mode, frames, H, W, C, *, da_c
     a.frames, a.H, a.W, a.C, a.lrelu, a.g_s2d = frames, H, W, C, int(lrelu), int(g_s2d)
     check(lib().srvp_bn_bwd_reduce(ctypes.byref(a), stream_ptr()), 'bn_bwd_reduce')
     c12 = torch.empty(2, C, dtype=torch.float32, device=dev)
+    c1p, c2p = _lib.c_ptr(c12.data_ptr()), _lib.c_ptr(c12.data_ptr() + 4 * C)     # rows of c12 without building two views
     count = float(frames * H * W)
     if sync:
         # SyncBatchNorm backward: dgamma / dbeta from the LOCAL sums (DDP averages them), the dx correction from the GLOBAL sums
         sync_bwd_finalize(partial, rows, C, count, c12, dgamma, dbeta)
     else:
-        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(c12[0]), ptr(c12[1]),
+        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), c1p, c2p,
                                         ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
-    check(lib().srvp_bn_bwd_apply(ctypes.byref(a), ptr(gamma), ptr(c12[0]), ptr(c12[1]), stream_ptr()), 'bn_bwd_apply')
-    n = float(frames * H * W * C)
-    _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0),
-             desc=f'F={frames} {H}x{W} C={C} da_mode={da_mode}' + (' skip' if skip is not None else '') + (' s2d' if g_s2d else ''))
+    check(lib().srvp_bn_bwd_apply(ctypes.byref(a), ptr(gamma), c1p, c2p, stream_ptr()), 'bn_bwd_apply')
+    if PROFILE is not None:
+        n = float(frames * H * W * C)
+        _account(0.0, 2.0 * n * 3 + 2.0 * 2 * n * (0.25 if da_mode == _lib.SRC_POOL2 else 4.0 if da_mode == _lib.SRC_UP2 else 1.0),
+                 desc=f'F={frames} {H}x{W} C={C} da_mode={da_mode}' + (' skip' if skip is not None else '') + (' s2d' if g_s2d else ''))
     return g
 
 
@@ -833,10 +838,14 @@ def gemm(a, b, c, *, bias=None, bias_on_m=False, act=_lib.ACT_NONE, accumulate=F
         planes = torch.empty(det_split, M, N, dtype=torch.float32, device=c.device)
         _gemm_call(a, b, planes[0], None, False, act, False, det_split, M * N)
         check(lib().srvp_sum_slices_f32(ptr(planes), ptr(c), c_int(det_split), c_i64(M * N), stream_ptr()), 'sum_slices')
+        if PROFILE is None:
+            return c
         _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N,
                  desc=f'M={M} N={N} K={K} det_split={det_split} a{tuple(a.stride())} b{tuple(b.stride())} {a.dtype} {b.dtype}')
         return c
     _gemm_call(a, b, c, bias, bias_on_m, act, accumulate, split_k, 0)
+    if PROFILE is None:
+        return c
     _account(2.0 * M * N * K, a.element_size() * M * K + b.element_size() * N * K + c.element_size() * M * N,
              desc=f'M={M} N={N} K={K} acc={int(accumulate)} a{tuple(a.stride())} b{tuple(b.stride())} {a.dtype} {b.dtype}')
     return c
