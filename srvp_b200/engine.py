@@ -276,6 +276,7 @@ class _DecCtx:
 # Split skip convolutions at or above this resolution add the per-video term as extra K stages ([hi | lo] bf16 x identity weights) instead
 # of in the epilogue. OFF by default: measured slower (64x64 layer 3.00 vs 2.49 ms, 32x32 1.88 vs 1.37 ms; step 56.7 vs 55.3 ms,
 # profiles/r03x_*): a tile then has three loader stages, each a full cp.async round trip, and only two halo buffers to hide them in.
+FWD_UNSPLIT_RES = int(__import__('os').environ.get('SRVP_FWD_UNSPLIT_RES', '64'))   # decoder layers at or above this resolution: forward not split
 ADD_HILO_MIN_RES = int(__import__('os').environ.get('SRVP_ADD_HILO_MIN_RES', '1000'))
 THIN_HEAD_WGRAD = int(__import__('os').environ.get('SRVP_THIN', '1'))   # decoder head: weight gradient from the raw z (csrc/thin.cu)
 HOLD_RES = int(__import__('os').environ.get('SRVP_WGRAD_HOLD_RES', '16'))   # decoder layers at or below this resolution: weight gradients held back
@@ -332,9 +333,28 @@ def _decoder_fwd(dec, dec_inp, skip_levels, frame_map, training, sigmoid=True, w
         if blk.skip_level is not None and sel is not None and F_ % sel.shape[0] == 0 and blk.cout % 64 == 0:
             nvid = sel.shape[0]
             s_src = _skip_src(skip_levels[blk.skip_level], sel)
+            alg = (h_src.channels + s_src.channels) / h_src.channels
+            if blk.res >= FWD_UNSPLIT_RES and frame_map is not None:
+                # FORWARD of the largest images in one launch over both sources (two K stages per tile, the skip half read through the
+                # frame map): with 64 channels the split launch is paced by its epilogue (per-video addend: 1.9 + 0.14 ms against ~1.3),
+                # not by the MMAs the split saves. The BACKWARD stays split: it needs the activated skip features per video only.
+                wp = ops.pack_conv3x3(blk.conv.weight, 'conv')
+                r = ops.conv3x3([h_src, _skip_src(skip_levels[blk.skip_level], frame_map)], wp, F_, blk.res, blk.res, blk.cout, stats=training,
+                                save_input=training, a_out_channels=h_src.channels)
+                a_s = ops.materialize(s_src, nvid, blk.res, blk.res) if training else None
+                c.split[li] = (a_s, s_src.channels, nvid)
+                z, partial = r[0], r[1]
+                if training:
+                    ops.bn_finalize(partial, float(F_ * blk.res * blk.res), blk.bn, st, training_update=want_stats_update)
+                else:
+                    ops.bn_eval_params(blk.bn, st)
+                c.z.append(z)
+                c.st.append(st)
+                c.srcs.append(r[2] if training else None)
+                prev = Src(z, blk.cout, st.scale, st.shift, None, 0, SRC_DIRECT, True)
+                continue
             wp_s = ops.pack_conv3x3(blk.conv.weight, 'conv', cin_range=(h_src.channels, s_src.channels))
             wp_h = ops.pack_conv3x3(blk.conv.weight, 'conv', cin_range=(0, h_src.channels))
-            alg = (h_src.channels + s_src.channels) / h_src.channels
             if blk.res >= ADD_HILO_MIN_RES:
                 # per-video term through the TENSOR CORE: stored as [hi | lo] bf16, read by the per-frame launch as a second source whose K
                 # stages multiply the centre tap only against identity weights (+22 % MMAs); ablation switch, see ADD_HILO_MIN_RES
