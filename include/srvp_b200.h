@@ -222,6 +222,9 @@ typedef struct {
   int32_t lrelu;
   int32_t g_s2d;          /* apply: write dz as its space-to-depth image (frames,H/2,W/2,4C), channel (py*2+px)*C + c */
 } srvp_bn_bwd_args;
+/* out (1, C, 2) = column sums of the (rows, C, 2) partial statistics (fp64 accumulation): what one rank contributes to the
+ * SyncBatchNorm all-reduce (train.py:283); srvp_bn_finalize consumes the all-reduced totals as rows = 1. */
+int srvp_bn_rows_sum(const float* partial, int32_t rows, int32_t C, float* out, void* stream);
 int srvp_bn_bwd_reduce_rows(int32_t frames, int32_t H, int32_t W, int32_t C, int32_t da_mode);
 int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* args, void* stream);
 int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,

@@ -118,7 +118,7 @@ EXPORTS = [
     'srvp_pack_conv3x3_weights', 'srvp_pack_conv3x3_multi', 'srvp_pack_conv4x4s2_weights', 'srvp_conv4x4s2_tap_mask', 'srvp_wgrad3x3', 'srvp_nchw_f32_to_nhwc_bf16',
     'srvp_nchw_f32_to_s2d_bf16', 'srvp_sigmoid_bwd_nchw_to_s2d16', 'srvp_nhwc_bf16_to_nchw_f32',
     'srvp_materialize_src', 'srvp_sum_over_time_bf16', 'srvp_sum_slices_f32', 'srvp_transpose_last2_f32', 'srvp_bn_finalize', 'srvp_bn_eval_params',
-    'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
+    'srvp_channel_stats_rows', 'srvp_channel_stats', 'srvp_bn_rows_sum', 'srvp_bn_bwd_reduce_rows', 'srvp_bn_bwd_reduce',
     'srvp_bn_bwd_finalize', 'srvp_bn_bwd_apply', 'srvp_sigmoid_bwd_nchw_to_nhwc16', 'srvp_gemm', 'srvp_bn_tanh_rows_fwd', 'srvp_bn_tanh_rows_bwd', 'srvp_rows_stats_f32', 'srvp_bn_tanh_rows_bwd_reduce',
     'srvp_bn_tanh_rows_bwd_apply',
     'srvp_u8_to_nhwc_bf16', 'srvp_u8_to_tbchw_f32', 'srvp_rsample_fwd', 'srvp_rsample_bwd', 'srvp_adam_chunk', 'srvp_adam_multi',

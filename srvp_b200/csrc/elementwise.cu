@@ -589,6 +589,31 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_flat_kernel(const BnBwdDev p, l
   }
 }
 
+// out[c][0..1] = sum over rows of partial[r][c][0..1] (fp64 accumulation, fp32 result): the per-rank totals that travel in the
+// SyncBatchNorm statistics all-reduce. Same block shape as bn_finalize_kernel.
+__global__ void __launch_bounds__(256) bn_rows_sum_kernel(const float* __restrict__ partial, int rows, int C, float* __restrict__ out) {
+  __shared__ double r1[8][32], r2[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) {
+    for (int r = rl; r < rows; r += 8) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * C + c) * 2));
+      s1 += v.x;
+      s2 += v.y;
+    }
+  }
+  r1[rl][cl] = s1;
+  r2[rl][cl] = s2;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s1 += r1[k][cl]; s2 += r2[k][cl]; }
+    out[(size_t)c * 2] = (float)s1;
+    out[(size_t)c * 2 + 1] = (float)s2;
+  }
+}
+
 // c1 = sum(g)/n, c2 = sum(g*xhat)/n; dgamma += sum(g*xhat), dbeta += sum(g). Same block shape as bn_finalize_kernel.
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float* __restrict__ c1,
                                                              float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -968,6 +993,12 @@ static int bn_bwd_launch(const srvp_bn_bwd_args* a, bool apply, const float* gam
 }
 
 extern "C" int srvp_bn_bwd_reduce(const srvp_bn_bwd_args* a, void* stream) { return bn_bwd_launch(a, false, nullptr, nullptr, nullptr, stream); }
+
+extern "C" int srvp_bn_rows_sum(const float* partial, int32_t rows, int32_t C, float* out, void* stream) {
+  SRVP_REQUIRE(partial != nullptr && out != nullptr && rows > 0 && C > 0, "bn_rows_sum: bad argument");
+  bn_rows_sum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, rows, C, out);
+  return check_launch("bn_rows_sum");
+}
 
 extern "C" int srvp_bn_bwd_finalize(const float* partial, int32_t rows, int32_t C, double count, float* c1, float* c2, float* dgamma, float* dbeta,
                                     void* stream) {

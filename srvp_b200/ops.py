@@ -690,7 +690,15 @@ def bn_finalize(partial, count, bn, state, training_update=True, eps=1e-5, momen
                                             ctypes.c_float(eps), ctypes.c_float(momentum), ptr(rm), ptr(rv), ptr(state.scale), ptr(state.shift),
                                             ptr(state.mean), ptr(state.invstd), stream_ptr()), 'bn_finalize_p2p')
             return state
-        partial, count = parallel.allreduce_bn_partial(partial, count)
+        if partial.is_cuda and torch.distributed.get_backend() == 'nccl':
+            # one launch for the per-rank totals (fp64 row sums -> fp32), one NCCL all-reduce, then the ordinary finalisation on rows = 1:
+            # the exchange sits on the critical path of every layer, each extra small launch there costs ~6 us x 84 per step
+            tot = torch.empty(1, partial.shape[1], 2, dtype=torch.float32, device=partial.device)
+            check(lib().srvp_bn_rows_sum(ptr(partial), c_int(partial.shape[0]), c_int(partial.shape[1]), ptr(tot), stream_ptr()), 'bn_rows_sum')
+            torch.distributed.all_reduce(tot)
+            partial, count = tot, float(count) * torch.distributed.get_world_size()
+        else:
+            partial, count = parallel.allreduce_bn_partial(partial, count)
     state.count = float(count)
     rows, C = partial.shape[0], partial.shape[1]
     check(lib().srvp_bn_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(bn.weight), ptr(bn.bias),
@@ -726,6 +734,13 @@ def sync_bwd_finalize(partial, rows, C, count, c12, dgamma, dbeta):
         check(lib().srvp_bn_bwd_finalize_p2p(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), peer.ptrs, c_int(peer.rank),
                                             c_int(peer.world), peer.next_seq(), ptr(c12[0]), ptr(c12[1]), ptr(dgamma), ptr(dbeta), stream_ptr()),
               'bn_bwd_finalize_p2p')
+        return
+    if partial.is_cuda and torch.distributed.get_backend() == 'nccl':
+        # every rank holds the same number of positions (train.py:218), so the global means c1, c2 are the AVERAGE of the local ones:
+        # local finalisation (dgamma / dbeta from the local sums, local means into c12) + one NCCL AVG all-reduce of c12
+        check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), _lib.c_ptr(c12.data_ptr()),
+                                        _lib.c_ptr(c12.data_ptr() + 4 * C), ptr(dgamma), ptr(dbeta), stream_ptr()), 'bn_bwd_finalize')
+        torch.distributed.all_reduce(c12, op=torch.distributed.ReduceOp.AVG)
         return
     scratch = torch.empty(2, C, dtype=torch.float32, device=partial.device)
     check(lib().srvp_bn_bwd_finalize(ptr(partial), c_int(rows), c_int(C), ctypes.c_double(count), ptr(scratch[0]), ptr(scratch[1]),
