@@ -28,15 +28,16 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors must have the C layout (checked against a tiny C program compiled with gcc)."""
     from srvp_b200 import _lib
-    src = '#include <stdio.h>\n#include "srvp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(srvp_conv_src), ' \
+    src = '#include <stdio.h>\n#include "srvp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(srvp_conv_src), ' \
           'sizeof(srvp_conv3x3_args), sizeof(srvp_wgrad3x3_args), sizeof(srvp_bn_bwd_args), sizeof(srvp_gemm_args), ' \
-          'sizeof(srvp_latent_fwd_args), sizeof(srvp_latent_bwd_args), sizeof(srvp_linear_args));return 0;}\n'
+          'sizeof(srvp_latent_fwd_args), sizeof(srvp_latent_bwd_args), sizeof(srvp_linear_args), sizeof(srvp_pack_job));return 0;}\n'
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, 't.c'), 'w').write(src)
         subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')], check=True)
         sizes = [int(v) for v in subprocess.run([os.path.join(d, 't')], capture_output=True, text=True, check=True).stdout.split()]
-    mirrors = [_lib.ConvSrc, _lib.Conv3x3Args, _lib.Wgrad3x3Args, _lib.BnBwdArgs, _lib.GemmArgs, _lib.LatentFwdArgs, _lib.LatentBwdArgs, _lib.LinearArgs]
+    mirrors = [_lib.ConvSrc, _lib.Conv3x3Args, _lib.Wgrad3x3Args, _lib.BnBwdArgs, _lib.GemmArgs, _lib.LatentFwdArgs, _lib.LatentBwdArgs, _lib.LinearArgs,
+               _lib.PackJob]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
@@ -197,3 +198,52 @@ def test_peer_bn_exchange_is_gated():
         assert parallel.PeerBN.get() is None      # no process group here
     finally:
         del os.environ['SRVP_BN_P2P']
+
+
+def test_pack_job_descriptions_and_pack_concatenation():
+    """Host logic of the packed-weight cache (ops._pack_job: what one srvp_pack_job of srvp_pack_conv3x3_multi describes) and of
+    ops.concat_packs (K stages of several operands back to back inside every N block); no kernel is launched."""
+    from srvp_b200 import ops
+    w = torch.zeros(128, 192, 3, 3)
+    # whole weight, forward and data-gradient operand
+    assert ops._pack_job(w, 'conv', None)[1:] == (128, 128, 192, 192, 192 * 9, 9, 0)
+    assert ops._pack_job(w, 'conv_dgrad', None)[1:] == (192, 192, 128, 128, 9, 192 * 9, 1)
+    # input-channel ranges (the two halves of a convolution over cat[h, skip]): K of the forward operand, N of the data-gradient one
+    p0, n_real, n_pad, k_real, k_pad, sn, sk, flip = ops._pack_job(w, 'conv', (64, 128))
+    assert p0 == w.data_ptr() + 4 * 64 * 9 and (n_real, n_pad, k_real, k_pad, sn, sk, flip) == (128, 128, 128, 128, 192 * 9, 9, 0)
+    assert ops._pack_job(w, 'conv_dgrad', (0, 64))[1:5] == (64, 64, 128, 128)
+    # thin operands are padded to 16, everything else to multiples of 64
+    assert ops._pack_job(torch.zeros(64, 3, 3, 3), 'conv', None)[2:5] == (64, 3, 16)
+    assert ops._pack_job(torch.zeros(64, 3, 3, 3), 'convT', None)[1:5] == (3, 16, 64, 64)
+    # concatenation: cout = 512 has two N blocks of 256; every block gets [stages of a | stages of b]
+    a = torch.arange(2 * 6, dtype=torch.float32).view(2, 6).reshape(-1)         # 2 blocks x 6 elements
+    b = 100 + torch.arange(2 * 4, dtype=torch.float32).view(2, 4).reshape(-1)   # 2 blocks x 4 elements
+    cat = ops.concat_packs([a, b], 512)
+    assert cat.tolist() == [0, 1, 2, 3, 4, 5, 100, 101, 102, 103, 6, 7, 8, 9, 10, 11, 104, 105, 106, 107]
+    assert ops.concat_packs([a, b], 128).tolist() == a.tolist() + b.tolist()    # one N block: plain concatenation
+
+
+def test_gradient_sinks_and_deferred_join_flag():
+    """parallel.GradBucket attaches flat-buffer views as p.grad / p._srvp_sink and switches the engine to the deferred join;
+    infer._direct_sinks / ops.grad_target only treat a parameter as an in-place sink while p.grad still IS that view."""
+    from srvp_b200 import ops, parallel, infer
+    old = ops.DEFER_JOIN
+    try:
+        ops.DEFER_JOIN = False
+        ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+        assert infer._direct_sinks(*ps) is None and ops.grad_target(ps[0])[1] is False
+        b = parallel.GradBucket(ps)
+        assert ops.DEFER_JOIN is True
+        assert b.flat.numel() == 16 + 8 and all(p.grad is v for p, v in zip(ps, b.views))     # 16-byte aligned views
+        sinks = infer._direct_sinks(ps[0], None, ps[1])
+        assert sinks[0] is b.views[0] and sinks[1] is None and sinks[2] is b.views[1]
+        assert ops.grad_target(ps[1]) == (b.views[1], True)
+        ps[1].grad = torch.zeros(7)                       # somebody replaced the gradient: no longer an in-place sink
+        assert infer._direct_sinks(*ps) is None and ops.grad_target(ps[1])[1] is False
+        b.zero()                                          # re-attaches the views
+        assert infer._direct_sinks(*ps) is not None
+        frozen = torch.nn.Parameter(torch.zeros(3), requires_grad=False)
+        frozen._srvp_sink = frozen.grad = None
+        assert infer._direct_sinks(frozen) is None
+    finally:
+        ops.DEFER_JOIN = old
