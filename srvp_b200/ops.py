@@ -374,8 +374,8 @@ def flush_wgrads(held=False):
 
 @contextlib.contextmanager
 def side_section(*keep):
-    """`with side_section(tensors...) as on_side:` -- launches inside run on the weight-gradient stream (behind everything enqueued on the
-    current stream so far) when every consumer of their results joins first, i.e. under a GradBucket (DEFER_JOIN); otherwise inline
+    """`with side_section(tensors...) as on_side:` -- launches inside run on the auxiliary (third) stream, behind everything enqueued on
+    the current stream so far, when every consumer of their results joins first, i.e. under a GradBucket (DEFER_JOIN); otherwise inline
     (on_side False). For parameter-gradient work that nothing on the critical path of the backward pass reads: the body must write
     only into buffers that outlive it (ops.grad_target views) and `keep` must list the tensors it reads."""
     if not (WGRAD_STREAM and DEFER_JOIN and PROFILE is None) or torch.cuda.is_current_stream_capturing():
